@@ -1,0 +1,159 @@
+/*
+ * swga_b200.h -- C ABI of libswga_b200.so: the B200 (sm_100a) implementation of swga's
+ * data-parallel hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (eclarke/swga, citations relative to its tree) has no FFI: its seams are Python
+ * functions and two subprocess protocols.  Each entry point below names the reference interface
+ * whose RESULTS it reproduces; INTEGRATION.md shows the ctypes stubs a swga maintainer would add
+ * to swga/kmers.py, swga/locate.py and swga/score.py.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative SWGA_E* code; swga_last_error() returns a
+ *     thread-local message for the last failing call on this thread
+ *   - pointers named d_* are device pointers (cudaMalloc / swga_malloc / torch data_ptr), h_* are
+ *     host pointers; all buffers are caller-owned unless stated
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - nucleotide code is DSK's: (byte >> 1) & 3  =>  A=0 C=1 T=2 G=3 (ext/dsk/minia/Kmer.cpp:18-24);
+ *     a k-mer code is the base-4 number whose most significant digit is the first base
+ *     (Kmer.cpp:65-76); reverse complement is digit reversal with digit ^ 2 (lut.h:8-10)
+ *   - "packed genome": uint32 words, 16 bases per word, first base in bits 31:30; plus a "break
+ *     mask": 1 bit per base (uint32 per 32 bases, first base in bit 31); bit i set means NO k-mer
+ *     window may contain both base i and base i+1 (record ends, mode-A 'N', genome end)
+ *   - count tables: uint32, direct-indexed by k-mer code, the tables for k = kmin..kmax
+ *     concatenated (swga_tables_words(kmin,kmax) words in total)
+ */
+#ifndef SWGA_B200_H
+#define SWGA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWGA_OK            0
+#define SWGA_E_CUDA       -1   /* a CUDA runtime call failed (message has the CUDA error string) */
+#define SWGA_E_ARG        -2   /* invalid argument */
+#define SWGA_E_NOMEM      -3   /* allocation failed */
+#define SWGA_E_FORMAT     -4   /* malformed input (e.g. not a FASTA image) */
+#define SWGA_E_OVERFLOW   -5   /* an output buffer supplied by the caller is too small */
+
+#define SWGA_KMAX_LIMIT   15   /* dense direct-indexed tables: 4^15 uint32 = 4 GiB */
+
+/* mask_mode of swga_pack */
+#define SWGA_MASK_NONE    0    /* DSK mode B: every byte is a base ('N' -> G), SortingCount.cpp:392-421 */
+#define SWGA_MASK_N       1    /* DSK mode A: upper-case 'N' splits reads, SortingCount.cpp:243-261   */
+#define SWGA_MASK_STRICT  2    /* locate: only upper-case A,C,G,T can match, swga/locate.py:76-90      */
+
+typedef struct swga_ctx swga_ctx;
+
+/* ---- library / context -------------------------------------------------------------------- */
+int         swga_abi_version(void);
+const char *swga_last_error(void);
+/* One context per (host thread, device).  Owns workspaces, two streams and events used by the
+ * *_host pipelines.  Fails with SWGA_E_CUDA when no CUDA device is usable: there is NO CPU path. */
+int  swga_ctx_create(int device, swga_ctx **out);
+void swga_ctx_destroy(swga_ctx *ctx);
+int  swga_ctx_sm_count(const swga_ctx *ctx);
+
+/* ---- memory helpers for hosts that do not bring their own allocator ------------------------- */
+int swga_malloc(swga_ctx *ctx, void **d_ptr, size_t bytes);
+int swga_free(swga_ctx *ctx, void *d_ptr);
+int swga_host_alloc(swga_ctx *ctx, void **h_ptr, size_t bytes);      /* pinned */
+int swga_host_free(swga_ctx *ctx, void *h_ptr);
+int swga_memset(swga_ctx *ctx, void *d_ptr, int value, size_t bytes, void *stream);
+int swga_h2d(swga_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int swga_d2h(swga_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int swga_stream_sync(swga_ctx *ctx, void *stream);
+
+/* ---- sizes ----------------------------------------------------------------------------------- */
+uint64_t swga_tables_words(int kmin, int kmax);            /* sum_{k=kmin..kmax} 4^k              */
+uint64_t swga_table_offset(int kmin, int k);               /* word offset of table k in the block */
+uint64_t swga_packed_words(uint64_t n_bases);              /* uint32 words swga_pack writes        */
+uint64_t swga_brk_words(uint64_t n_bases);                 /* uint32 words of the break mask       */
+
+/* ---- host-side FASTA reader (native host code; no GPU) ---------------------------------------
+ * Replaces DSK's Bank::get_next_seq_from_file (ext/dsk/minia/Bank.cpp:150-209): records start at a
+ * '>' or '@' that begins a line, lines are joined, one trailing '\r' per line is dropped under
+ * Bank.cpp:124-125's rule.  Pass 1 (h_seq == NULL) returns sizes; pass 2 fills the buffers.
+ *   h_seq        [*n_bases]   joined sequence bytes of all records, no separators
+ *   h_rec_starts [*n_rec + 1] start of each record in h_seq, last entry = *n_bases
+ *   h_name_off   [*n_rec * 2] (offset, length) into the file image of each record's first header
+ *                             token (pyfaidx's record key, relied on by swga/locate.py:42)
+ */
+int swga_fasta_scan(const uint8_t *h_file, uint64_t n_file, uint8_t *h_seq, uint64_t *h_rec_starts,
+                    uint64_t *h_name_off, uint64_t *n_bases, uint64_t *n_rec);
+/* DSK's read-mode choice: 1 (mode B, raw) iff one of the first 10,001 records is longer than
+ * 1,000,000 bases (Bank.cpp:470-494, SortingCount.cpp:81-82); else 0 (mode A, split at 'N'). */
+int swga_dsk_mode(const uint64_t *h_rec_starts, uint64_t n_rec);
+
+/* ---- kernel (a): 2-bit pack -------------------------------------------------------------------
+ * Replaces NT2int/code4NT/BinaryReads::write_read (Kmer.cpp:18-43, Bank.cpp:832-885) and the N-split
+ * (SortingCount.cpp:243-261).  d_ascii must be 16-byte aligned.  Writes swga_packed_words(n) words
+ * of d_packed and swga_brk_words(n) words of d_brk (mask per `mask_mode`, plus the end-of-buffer
+ * break on base n-1). */
+int swga_pack(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, int mask_mode,
+              uint32_t *d_packed, uint32_t *d_brk, void *stream);
+/* ORs record boundaries into the break mask: for every r in 1..n_rec-1 sets the bit of base
+ * d_rec_starts[r]-1 (k-mers never span records: one DSK "read" per record, Bank.cpp:150-209;
+ * swga/locate.py:43-47 searches per record).  Entries outside (0, n] are ignored. */
+int swga_mark_records(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64_t n_rec, uint64_t n,
+                      uint32_t *d_brk, void *stream);
+
+/* ---- kernel (b): all-k counting ----------------------------------------------------------------
+ * Replaces compute_kmer_table_from_one_seq / KmersBuffer::readkmers + OAHash::increment
+ * (Bank.cpp:889-902,1042-1070, OAHash.cpp:142-154) for every k in [kmin,kmax] at once.
+ *
+ * swga_count_accumulate ADDS, for each start position p < n_starts, one count to the forward-code
+ * table of v = min(kmax, run of break-free bases from p), if v >= kmin ("top-k + tails" form).
+ * The caller zeroes d_tables first and may accumulate several chunks / GPUs (the form is additive:
+ * an allreduce-sum across ranks may be applied to it).  The buffers must hold the kmax-1 bases
+ * after the last owned start (right halo) or end with a break.
+ * swga_count_finalize turns the accumulated block into full forward tables in place:
+ *   T_k[x] += sum_b T_{k+1}[4x+b]   for k = kmax-1 .. kmin.
+ * swga_fold_canonical writes DSK's canonical counts (Kmer.cpp:122: min(fwd, revcomp)):
+ *   C_k[x] = T_k[x] + T_k[rc(x)] if x < rc(x);  T_k[x] if x == rc(x);  0 otherwise.
+ */
+int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk,
+                          uint64_t n_starts, int kmin, int kmax, uint32_t *d_tables, void *stream);
+int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *d_tables, void *stream);
+int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd,
+                        uint32_t *d_canon, void *stream);
+
+/* Whole counting pass on a device-resident genome: pack + mark + accumulate + finalize + fold,
+ * using context-owned workspaces.  d_canon (and d_fwd if non-NULL) receive swga_tables_words()
+ * words.  `finalize` = 0 leaves d_fwd in the additive form and skips the fold (multi-GPU: allreduce
+ * d_fwd, then call swga_count_finalize + swga_fold_canonical). */
+int swga_count_genome_device(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n,
+                             const uint64_t *d_rec_starts, uint64_t n_rec, int mask_mode,
+                             int kmin, int kmax, uint64_t n_starts, int finalize,
+                             uint32_t *d_fwd, uint32_t *d_canon, void *stream);
+
+/* The call swga/kmers.py:42-46 would make instead of spawning `dsk`, for all k at once, with HOST
+ * buffers: streams h_seq to the device in chunks (H2D overlapped with pack/count), returns the
+ * canonical tables in h_canon.  mode_b as returned by swga_dsk_mode. */
+int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n,
+                           const uint64_t *h_rec_starts, uint64_t n_rec, int mode_b,
+                           int kmin, int kmax, uint32_t *h_canon);
+
+/* DSK result-file writer (ext/dsk/minia/SortingCount.cpp:149-156,649-653; read back by
+ * swga/kmers.py:94-115): [i32 64][i32 k] then (u64 code, u32 count) for every count >= threshold. */
+int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,
+                        uint64_t *n_written);
+
+/* ---- synthetic genomes (SURVEY.md 8d generator, bit-identical to swga_b200/synth.py) ----------- */
+int swga_synth_bases(swga_ctx *ctx, uint64_t seed, uint64_t start, uint64_t n,
+                     uint32_t t_a, uint32_t t_c, uint32_t t_g, uint8_t *d_ascii, void *stream);
+
+/* ---- atomic-throughput microbenchmarks (the A_peak of SURVEY.md 8d) ----------------------------
+ * Issues n_ops uniformly random red.global.add.u32 on a table of `table_words` words (global) or
+ * shared-memory atomics on a per-CTA table of `table_words` words; returns milliseconds. */
+int swga_bench_red_global(swga_ctx *ctx, uint32_t *d_table, uint64_t table_words, uint64_t n_ops,
+                          float *ms);
+int swga_bench_atom_shared(swga_ctx *ctx, uint32_t table_words, uint64_t n_ops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWGA_B200_H */

@@ -1,0 +1,354 @@
+// abi.cu -- context, memory helpers, host-side FASTA reader, and the whole-genome counting
+// pipelines (device-resident and host-buffer) of libswga_b200.so.
+#include <ctype.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+int swga_mark_records_origin(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64_t n_rec, uint64_t origin,
+                             uint64_t n, uint32_t *d_brk, cudaStream_t stream);
+
+// ---- errors ---------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void swga_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *swga_last_error(void) { return g_err; }
+extern "C" int swga_abi_version(void) { return 1; }
+
+// ---- context --------------------------------------------------------------------------------
+extern "C" int swga_ctx_create(int device, swga_ctx **out)
+{
+    ARG_CHECK(out);
+    *out = nullptr;
+    int n_dev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) {
+        swga_set_error("device %d not available (%d CUDA devices); libswga_b200 has no CPU path", device, n_dev);
+        return SWGA_E_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    swga_ctx *c = new swga_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        swga_set_error("device %d is sm_%d%d; libswga_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        delete c;
+        return SWGA_E_CUDA;
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return SWGA_OK;
+}
+
+static void free_buf(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" void swga_ctx_destroy(swga_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_buf(c->packed); free_buf(c->brk); free_buf(c->fwd); free_buf(c->canon); free_buf(c->recs);
+    free_buf(c->scratch);
+    for (int i = 0; i < 2; ++i) {
+        free_buf(c->ascii[i]); free_buf(c->packed2[i]); free_buf(c->brk2[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    delete c;
+}
+
+extern "C" int swga_ctx_sm_count(const swga_ctx *c) { return c ? c->sm_count : 0; }
+
+int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return SWGA_OK;
+    if (b.p) CUDA_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        swga_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return SWGA_E_NOMEM;
+    }
+    b.cap = want;
+    return SWGA_OK;
+}
+
+// ---- memory helpers -------------------------------------------------------------------------
+extern "C" int swga_malloc(swga_ctx *ctx, void **d_ptr, size_t bytes)
+{
+    ARG_CHECK(ctx && d_ptr);
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        swga_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return SWGA_E_NOMEM;
+    }
+    return SWGA_OK;
+}
+extern "C" int swga_free(swga_ctx *ctx, void *d_ptr)
+{
+    ARG_CHECK(ctx);
+    CUDA_TRY(cudaFree(d_ptr));
+    return SWGA_OK;
+}
+extern "C" int swga_host_alloc(swga_ctx *ctx, void **h_ptr, size_t bytes)
+{
+    ARG_CHECK(ctx && h_ptr);
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        swga_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return SWGA_E_NOMEM;
+    }
+    return SWGA_OK;
+}
+extern "C" int swga_host_free(swga_ctx *ctx, void *h_ptr)
+{
+    ARG_CHECK(ctx);
+    CUDA_TRY(cudaFreeHost(h_ptr));
+    return SWGA_OK;
+}
+extern "C" int swga_memset(swga_ctx *ctx, void *d_ptr, int value, size_t bytes, void *stream)
+{
+    ARG_CHECK(ctx && (d_ptr || bytes == 0));
+    CUDA_TRY(cudaMemsetAsync(d_ptr, value, bytes, as_stream(stream)));
+    return SWGA_OK;
+}
+extern "C" int swga_h2d(swga_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+    ARG_CHECK(ctx && ((d_dst && h_src) || bytes == 0));
+    CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return SWGA_OK;
+}
+extern "C" int swga_d2h(swga_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+    ARG_CHECK(ctx && ((h_dst && d_src) || bytes == 0));
+    CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return SWGA_OK;
+}
+extern "C" int swga_stream_sync(swga_ctx *ctx, void *stream)
+{
+    ARG_CHECK(ctx);
+    CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    return SWGA_OK;
+}
+
+// ---- host FASTA reader ----------------------------------------------------------------------
+// Line-oriented formulation of the record rules of ext/dsk/minia/Bank.cpp:150-209:
+//   * the image must begin with '>' or '@' (Bank.cpp:284-299: anything else is taken for a list of
+//     file names); an empty image has no records
+//   * a line whose first byte is '>' or '@' (or 0xFF, which the reference's signed-char reader
+//     mistakes for EOF and then resumes from as a header, Bank.cpp:66-72,170) starts a record and
+//     is a header line; every other non-empty line is sequence and is appended whole
+//   * after appending a line, one trailing '\r' is dropped if the record is then longer than one
+//     byte (Bank.cpp:124-125)
+//   * '+' at line start would switch the reference to FASTQ: rejected here
+static inline bool is_rec_start(uint8_t c) { return c == '>' || c == '@' || c == 0xFF; }
+
+extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uint64_t *h_rec_starts,
+                               uint64_t *h_hdr, uint64_t *n_bases, uint64_t *n_rec)
+{
+    ARG_CHECK((f || n == 0) && n_bases && n_rec);
+    const bool fill = h_seq != nullptr || h_rec_starts != nullptr;
+    uint64_t total = 0, rec = 0;
+    if (n > 0 && f[0] != '>' && f[0] != '@') {
+        swga_set_error("not a FASTA image: first byte is 0x%02x, expected '>' (DSK would read it as a list of file names)",
+                       f[0]);
+        return SWGA_E_FORMAT;
+    }
+    uint64_t pos = 0;
+    uint64_t rec_len = 0;
+    while (pos < n) {
+        const uint8_t c = f[pos];
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + pos, '\n', n - pos));
+        const uint64_t eol = nl ? (uint64_t)(nl - f) : n;      // index of '\n' or n
+        if (is_rec_start(c)) {
+            if (fill && h_rec_starts) h_rec_starts[rec] = total;
+            if (fill && h_hdr) {
+                h_hdr[2 * rec] = pos + 1;
+                h_hdr[2 * rec + 1] = eol - (pos + 1);
+            }
+            // The reference reads the header TOKEN with an isspace() delimiter and only then the rest
+            // of the line: when the token's delimiter is itself '\n' the header ends there.  A '\v',
+            // '\f' or '\r' delimiter is followed by "rest of line", same as here.
+            rec++;
+            rec_len = 0;
+        } else if (c == '+') {
+            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported", (unsigned long long)pos);
+            return SWGA_E_FORMAT;
+        } else if (eol > pos) {
+            const uint64_t len = eol - pos;
+            if (h_seq) memcpy(h_seq + total, f + pos, len);
+            total += len;
+            rec_len += len;
+            if (rec_len > 1 && f[eol - 1] == '\r') {
+                total--;
+                rec_len--;
+            }
+        }
+        pos = eol + 1;
+    }
+    if (fill && h_rec_starts) h_rec_starts[rec] = total;
+    *n_bases = total;
+    *n_rec = rec;
+    return SWGA_OK;
+}
+
+extern "C" int swga_dsk_mode(const uint64_t *h_rec_starts, uint64_t n_rec)
+{
+    if (!h_rec_starts) return 0;
+    const uint64_t lim = n_rec < 10001 ? n_rec : 10001;
+    uint64_t mx = 0;
+    for (uint64_t r = 0; r < lim; ++r) mx = std::max(mx, h_rec_starts[r + 1] - h_rec_starts[r]);
+    return mx > 1000000 ? 1 : 0;
+}
+
+// ---- whole-genome counting, device-resident input -------------------------------------------
+extern "C" int swga_count_genome_device(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, const uint64_t *d_rec_starts,
+                                        uint64_t n_rec, int mask_mode, int kmin, int kmax, uint64_t n_starts,
+                                        int finalize, uint32_t *d_fwd, uint32_t *d_canon, void *stream)
+{
+    ARG_CHECK(ctx && (d_ascii || n == 0) && n_starts <= n);
+    ARG_CHECK(d_fwd || finalize);
+    ARG_CHECK(d_canon || !finalize);
+    const uint64_t words = swga_tables_words(kmin, kmax);
+    TRY(swga_ensure(ctx, ctx->packed, swga_packed_words(n) * 4));
+    TRY(swga_ensure(ctx, ctx->brk, swga_brk_words(n) * 4));
+    if (!d_fwd) {
+        TRY(swga_ensure(ctx, ctx->fwd, words * 4));
+        d_fwd = (uint32_t *)ctx->fwd.p;
+    }
+    uint32_t *packed = (uint32_t *)ctx->packed.p, *brk = (uint32_t *)ctx->brk.p;
+    CUDA_TRY(cudaMemsetAsync(d_fwd, 0, words * 4, as_stream(stream)));
+    TRY(swga_pack(ctx, d_ascii, n, mask_mode, packed, brk, stream));
+    if (n_rec > 1) TRY(swga_mark_records(ctx, d_rec_starts + 1, n_rec - 1, n, brk, stream));
+    TRY(swga_count_accumulate(ctx, packed, brk, n_starts, kmin, kmax, d_fwd, stream));
+    if (finalize) {
+        TRY(swga_count_finalize(ctx, kmin, kmax, d_fwd, stream));
+        TRY(swga_fold_canonical(ctx, kmin, kmax, d_fwd, d_canon, stream));
+    }
+    return SWGA_OK;
+}
+
+// ---- whole-genome counting, host buffers (what swga/kmers.py would call instead of `dsk`) -----
+// The genome is cut into chunks of CHUNK start positions; chunk i needs bases
+// [a_i, min(n, b_i + kmax - 1)).  H2D of chunk i+1 (stream s_copy) overlaps pack + count of chunk i
+// (stream s_comp) through two staging buffers.
+extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n, const uint64_t *h_rec_starts,
+                                      uint64_t n_rec, int mode_b, int kmin, int kmax, uint32_t *h_canon)
+{
+    ARG_CHECK(ctx && (h_seq || n == 0) && h_canon && (h_rec_starts || n_rec == 0));
+    if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
+        swga_set_error("need 2 <= kmin <= kmax <= %d", SWGA_KMAX_LIMIT);
+        return SWGA_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t CHUNK = 64ull << 20;                        // start positions per chunk (multiple of 32)
+    const uint64_t words = swga_tables_words(kmin, kmax);
+    const int mask_mode = mode_b ? SWGA_MASK_NONE : SWGA_MASK_N;
+    TRY(swga_ensure(ctx, ctx->fwd, words * 4));
+    TRY(swga_ensure(ctx, ctx->canon, words * 4));
+    const uint64_t cap = std::min<uint64_t>(n, CHUNK + 64);
+    for (int i = 0; i < 2; ++i) {
+        TRY(swga_ensure(ctx, ctx->ascii[i], cap + 64));
+        TRY(swga_ensure(ctx, ctx->packed2[i], swga_packed_words(cap) * 4));
+        TRY(swga_ensure(ctx, ctx->brk2[i], swga_brk_words(cap) * 4));
+    }
+    if (n_rec > 0) {
+        TRY(swga_ensure(ctx, ctx->recs, (n_rec + 1) * 8));
+        CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, h_rec_starts, (n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->s_comp));
+    }
+    uint32_t *fwd = (uint32_t *)ctx->fwd.p, *canon = (uint32_t *)ctx->canon.p;
+    CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
+    int it = 0;
+    for (uint64_t a = 0; a < n; a += CHUNK, ++it) {
+        const int b = it & 1;
+        const uint64_t e_starts = std::min(n, a + CHUNK);      // owned starts [a, e_starts)
+        const uint64_t e_bases = std::min(n, e_starts + (uint64_t)kmax - 1);
+        const uint64_t len = e_bases - a;
+        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(ctx->ascii[b].p, h_seq + a, len, cudaMemcpyHostToDevice, ctx->s_copy));
+        CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
+        uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
+        TRY(swga_pack(ctx, (const uint8_t *)ctx->ascii[b].p, len, mask_mode, packed, brk, ctx->s_comp));
+        if (n_rec > 1) {
+            // records whose start s satisfies a < s <= a + len
+            const uint64_t *lo = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, a);
+            const uint64_t *hi = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, a + len);
+            if (hi > lo)
+                TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p + (lo - h_rec_starts),
+                                             (uint64_t)(hi - lo), a, len, brk, ctx->s_comp));
+        }
+        TRY(swga_count_accumulate(ctx, packed, brk, e_starts - a, kmin, kmax, fwd, ctx->s_comp));
+        CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
+    }
+    TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
+    TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
+    CUDA_TRY(cudaMemcpyAsync(h_canon, canon, words * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    return SWGA_OK;
+}
+
+// ---- DSK result file ------------------------------------------------------------------------
+extern "C" int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,
+                                   uint64_t *n_written)
+{
+    ARG_CHECK(path && h_canon_k && k >= 1 && k <= SWGA_KMAX_LIMIT);
+    FILE *fp = fopen(path, "wb");
+    if (!fp) {
+        swga_set_error("cannot open %s for writing", path);
+        return SWGA_E_ARG;
+    }
+    const int32_t hdr[2] = {64, k};
+    fwrite(hdr, 4, 2, fp);
+    const uint64_t n = 1ull << (2 * k);
+    const uint32_t thr = threshold ? threshold : 1;
+    std::vector<uint8_t> buf;
+    buf.reserve(12 * 65536);
+    uint64_t cnt = 0;
+    for (uint64_t c = 0; c < n; ++c) {
+        const uint32_t v = h_canon_k[c];
+        if (v < thr || v > 2147483646u) continue;              // max_couv, ext/dsk/minia/Utils.cpp:6
+        uint8_t rec[12];
+        memcpy(rec, &c, 8);
+        memcpy(rec + 8, &v, 4);
+        buf.insert(buf.end(), rec, rec + 12);
+        ++cnt;
+        if (buf.size() >= 12 * 65536) {
+            fwrite(buf.data(), 1, buf.size(), fp);
+            buf.clear();
+        }
+    }
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), fp);
+    if (fclose(fp) != 0) {
+        swga_set_error("write to %s failed", path);
+        return SWGA_E_ARG;
+    }
+    if (n_written) *n_written = cnt;
+    return SWGA_OK;
+}

@@ -1,0 +1,65 @@
+// common.cuh -- shared declarations for libswga_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/swga_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libswga_b200 is written for sm_100a (B200) only"
+#endif
+
+// ---- error plumbing -------------------------------------------------------------------------
+void swga_set_error(const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            swga_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                           __FILE__, __LINE__);                                          \
+            return SWGA_E_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+#define ARG_CHECK(cond)                                                                  \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            swga_set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__);   \
+            return SWGA_E_ARG;                                                           \
+        }                                                                                \
+    } while (0)
+#define TRY(expr)                                                                        \
+    do {                                                                                 \
+        int _r = (expr);                                                                 \
+        if (_r != SWGA_OK) return _r;                                                    \
+    } while (0)
+
+// ---- context --------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct swga_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;   // used by the *_host pipelines
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    DevBuf packed, brk, ascii[2], packed2[2], brk2[2], fwd, canon, recs, scratch;
+};
+
+int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes);   // grow-only workspace
+
+struct TableOffs {
+    unsigned long long off[SWGA_KMAX_LIMIT + 2];   // off[k] = word offset of table k (k >= kmin)
+};
+TableOffs swga_make_offs(int kmin, int kmax);
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline unsigned grid_for(uint64_t n_threads, unsigned block)
+{
+    uint64_t g = (n_threads + block - 1) / block;
+    return (unsigned)(g ? g : 1);
+}

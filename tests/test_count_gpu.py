@@ -1,0 +1,154 @@
+"""GPU parity for kernels (a)+(b): the CUDA path through the C ABI vs the CPU oracle, bit-exact,
+on the golden cases (real-DSK answers), seeded synthetic genomes, and size-independent properties."""
+import numpy as np
+import pytest
+
+from helpers import golden_case_bytes, table_digest
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["edge_a", "synth_mode_a", "synth_mode_b"]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+def u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_call_matches_oracle_and_real_dsk(case, oracle, dsk_golden, torch_cuda):
+    from swga_b200 import fasta, kmers
+    data = golden_case_bytes(case)
+    g = fasta.parse_fasta_bytes(data)
+    seq, rs = oracle.fasta_parse_dsk(data)
+    assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs)
+    kmin, kmax = (3, 12) if case == "edge_a" else (5, 12)
+    tabs = kmers.count_all(g, kmin, kmax)
+    for k in range(kmin, kmax + 1):
+        want = oracle.count_dense(seq, rs, k)
+        got = tabs.table(k)
+        assert np.array_equal(got, want), (case, k, int(np.count_nonzero(got != want)))
+        gold = dsk_golden[case].get(str(k))
+        if gold:
+            assert table_digest(got, k) == (gold["distinct"], gold["sum"], gold["md5"])
+
+
+@pytest.mark.parametrize("kmin,kmax", [(5, 12), (2, 4), (7, 7), (6, 13), (12, 12)])
+def test_k_ranges(kmin, kmax, oracle, torch_cuda):
+    from swga_b200 import fasta, kmers
+    data = golden_case_bytes("synth_mode_a")
+    g = fasta.parse_fasta_bytes(data)
+    tabs = kmers.count_all(g, kmin, kmax)
+    for k in range(kmin, kmax + 1):
+        assert np.array_equal(tabs.table(k), oracle.count_dense(g.seq, g.rec_starts, k)), k
+
+
+def test_empty_and_tiny_inputs(oracle, torch_cuda):
+    from swga_b200 import fasta, kmers
+    for fa in (b"", b">only_header\n", b">x\nACG\n", b">x\nACGTA\n", b">a\nAC\n>b\nGT\n>c\nACGTAC\n", b">n\nNNNNNNNN\n"):
+        g = fasta.parse_fasta_bytes(fa)
+        tabs = kmers.count_all(g, 3, 6)
+        for k in range(3, 7):
+            assert np.array_equal(tabs.table(k), oracle.count_dense(g.seq, g.rec_starts, k)), (fa, k)
+
+
+def test_device_path_synthetic_c1(oracle, torch_cuda):
+    """BASELINE config 1 sizes (1 Mbp fg, 10 Mbp bg), generated on the device by k_synth and on the
+    CPU by swga_b200.synth -- the generators must agree bit for bit, then the counts must."""
+    torch = torch_cuda
+    from swga_b200 import _lib, kmers, synth
+    lib, ctx = _lib.load(), _lib.context(0)
+    for name in ("C1_fg", "C1_bg"):
+        seed, n, gc, n_rec = synth.CONFIGS[name]
+        ta, tc, tg = synth.thresholds(gc)
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.swga_synth_bases(ctx.h, seed, 0, n, ta, tc, tg, _lib.ptr(d), None))
+        torch.cuda.synchronize()
+        h = synth.bases(seed, 0, n, gc)
+        assert np.array_equal(d.cpu().numpy(), h)
+        rs = synth.equal_records(n, n_rec)
+        fwd, canon = kmers.count_all_device(d, rs, mode_b=n > 1000000)
+        torch.cuda.synchronize()
+        got = u32(canon)
+        want = oracle.count_dense_allk(h, rs, 5, 12, mode_b=int(n > 1000000))
+        assert np.array_equal(got, want)
+
+
+def test_chunked_pipeline_crosses_chunk_boundaries(oracle, torch_cuda):
+    """> 64 Mi bases so swga_count_genome_host runs 2 chunks; records and N runs straddle the cut."""
+    from swga_b200 import fasta, kmers, synth
+    n = (64 << 20) + 5_000_000
+    seq = synth.bases(77, 0, n, 0.45)
+    cut = 64 << 20
+    seq[cut - 3:cut + 2] = ord("N")
+    rs = np.array([0, 1000, cut - 40, cut + 5, cut + 6, n - 7, n], dtype=np.uint64)
+    for mode_a in (True, False):
+        starts = rs if not mode_a else np.array(sorted(set(list(range(0, n, 900_000)) + [int(x) for x in rs])),
+                                                 dtype=np.uint64)
+        g = fasta.Genome(seq, starts, ["r%d" % i for i in range(len(starts) - 1)])
+        assert g.dsk_mode_b == (not mode_a)
+        tabs = kmers.count_all(g, 5, 12)
+        for k in (5, 8, 11, 12):
+            assert np.array_equal(tabs.table(k), oracle.count_dense(seq, starts, k)), (mode_a, k)
+
+
+def test_sharded_accumulate_equals_whole(oracle, torch_cuda):
+    """Chunk + right-halo sharding as swga_b200.dist does it, emulated on one GPU: accumulating the
+    shards of 2, 4 and 8 'ranks' into one table block equals the unsharded count."""
+    torch = torch_cuda
+    from swga_b200 import dist, kmers, synth
+    n = 3_000_017
+    seq = synth.bases(5, 0, n, 0.194)
+    seq[1_500_000:1_500_010] = ord("N")
+    rs = np.array([0, 17, 750_001, 750_002, 2_250_000, n], dtype=np.uint64)
+    want = oracle.count_dense_allk(seq, rs, 5, 12, mode_b=0)
+    for world in (1, 2, 4, 8):
+        total = None
+        for rank in range(world):
+            sh = dist.shard_genome(seq, rs, rank, world, kmax=12)
+            d = torch.from_numpy(sh.seq.copy()).cuda()
+            fwd, _ = kmers.count_all_device(d, sh.rec_starts, mode_b=False, n_starts=sh.n_starts, finalize=False)
+            total = fwd.clone() if total is None else total + fwd
+        canon = dist.finalize_tables(total, 5, 12)
+        torch.cuda.synchronize()
+        assert np.array_equal(u32(canon), want), world
+
+
+def test_properties_at_scale(torch_cuda):
+    """Size-independent checks on a 400 Mbp device-generated genome (no CPU oracle at this size):
+    sum of counts per k == sum over records of max(0, len-k+1); every non-canonical slot is 0;
+    table k is the marginal of table k+1 up to the per-record tails."""
+    torch = torch_cuda
+    from swga_b200 import _lib, kmers, synth
+    lib, ctx = _lib.load(), _lib.context(0)
+    n, n_rec, gc = 400_000_000, 7, 0.41
+    ta, tc, tg = synth.thresholds(gc)
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.swga_synth_bases(ctx.h, 4, 0, n, ta, tc, tg, _lib.ptr(d), None))
+    rs = synth.equal_records(n, n_rec)
+    fwd, canon = kmers.count_all_device(d, rs, mode_b=True)
+    torch.cuda.synchronize()
+    fwd, canon = u32(fwd), u32(canon)
+    lens = np.diff(rs.astype(np.int64))
+    for k in range(5, 13):
+        o0, o1 = int(lib.swga_table_offset(5, k)), int(lib.swga_table_offset(5, k + 1))
+        expect = int(np.maximum(0, lens - k + 1).sum())
+        assert int(fwd[o0:o1].astype(np.int64).sum()) == expect
+        assert int(canon[o0:o1].astype(np.int64).sum()) == expect
+        codes = np.arange(4 ** k, dtype=np.uint64)
+        rc = np.zeros_like(codes)
+        c = codes.copy()
+        for _ in range(k):
+            rc = (rc << np.uint64(2)) | ((c & np.uint64(3)) ^ np.uint64(2))
+            c >>= np.uint64(2)
+        assert not canon[o0:o1][codes > rc].any()
+        if k < 12:
+            up = fwd[o1:o1 + 4 ** (k + 1)].astype(np.int64).reshape(-1, 4).sum(1)
+            diff = fwd[o0:o1].astype(np.int64) - up
+            assert (diff >= 0).all() and int(diff.sum()) == n_rec      # one tail k-mer per record per level
