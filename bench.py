@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the swga hot path on B200.
+
+Metric (BASELINE.json): Gbases/s of all-k (k = 5..12) both-strand counting.  One "step" = one pass of
+the counting path over the workload: pack + mark + accumulate (+ NCCL allreduce at N > 1) + finalize +
+fold for the foreground AND the background genome, producing the canonical tables of both.
+
+Workload at every N: BASELINE.json configs[1] (= C2): synthetic 4.4 Mbp GC-rich foreground, 3.1 Gbp
+human-sized background (SURVEY.md 8d generator).  At N > 1 the background is sharded by contiguous
+chunk with an 11-base halo (strong scaling: total work fixed), the foreground is replicated.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KMIN, KMAX = 5, 12
+METRIC = "allk_count_throughput"
+UNIT = "Gbases/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--bg-bases", type=float, default=None, help="override background size (debug only)")
+    ap.add_argument("--cpu-sample-bases", type=int, default=600_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own DSK binary (oracle/_ref/dsk) + the restated Python record parser
+# ------------------------------------------------------------------------------------------------
+
+def _dsk_one(args):
+    fa, k, tmp = args
+    from oracle import swga_oracle as O
+    out = O.run_dsk(fa, k, tmp)
+    n = sum(1 for _ in O.parse_kmer_binary(out))          # swga/kmers.py:52-54 builds the dict from it
+    os.remove(out)
+    return n
+
+
+def cpu_reference_pass(workload, sample_bases, parallel):
+    """One pass of the reference CPU path (dsk k=5..12 + record parsing) over a bounded sample of the
+    workload's background genome.  Returns (seconds, bases, kind, cores)."""
+    from oracle import swga_oracle as O
+    from swga_b200 import synth
+    seed, n, gc, n_rec = synth.CONFIGS[workload + "_bg"]
+    sample = min(sample_bases, n)
+    seq = synth.bases(seed, 0, sample, gc)
+    have_dsk = os.access(os.path.join(ROOT, "oracle", "_ref", "dsk"), os.X_OK)
+    with tempfile.TemporaryDirectory() as tmp:
+        if have_dsk:
+            fa = os.path.join(tmp, "sample.fa")
+            synth.write_fasta(fa, seq, synth.equal_records(sample, 1))
+            jobs = [(fa, k, tmp) for k in range(KMIN, KMAX + 1)]
+            t0 = time.perf_counter()
+            if parallel > 1:
+                import multiprocessing as mp
+                with mp.get_context("fork").Pool(parallel) as pool:
+                    pool.map(_dsk_one, jobs)
+            else:
+                for j in jobs:
+                    _dsk_one(j)
+            dt = time.perf_counter() - t0
+            return dt, sample, "reference", max(1, parallel)
+        rs = synth.equal_records(sample, 1)
+        t0 = time.perf_counter()
+        O.count_dense_allk(seq, rs, KMIN, KMAX)
+        return time.perf_counter() - t0, sample, "port", 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(KMAX - KMIN + 1, os.cpu_count() or 1)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        dt, bases, kind, used = cpu_reference_pass(args.workload, args.cpu_sample_bases, cores)
+        if i >= args.warmup:
+            vals.append(dt)
+    ms = 1e3 * sum(vals) / len(vals)
+    value = bases / (ms * 1e-3) / 1e9
+    sample = ("%d-base prefix of the %s background, dsk k=5..12 as %d concurrent processes (the reference runs "
+              "them one after another on one core) + Python record parser" % (bases, args.workload, used))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "sample_bases": bases},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w):
+    from swga_b200 import synth
+    fg, bg = synth.CONFIGS[w + "_fg"], synth.CONFIGS[w + "_bg"]
+    return "%s: synthetic %.1f Mbp fg (gc %.3f) + %.1f Mbp bg (gc %.2f, %d records), all-k %d..%d both strands" % (
+        w, fg[1] / 1e6, fg[2], bg[1] / 1e6, bg[2], bg[3], KMIN, KMAX)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, timeout=5).stdout.decode()
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    from swga_b200 import _lib, dist, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("nccl", device_id=dev)
+    lib, ctx = _lib.load(), _lib.context(local)
+    P = _lib.ptr
+
+    fg_seed, n_fg, fg_gc, fg_nrec = synth.CONFIGS[args.workload + "_fg"]
+    bg_seed, n_bg, bg_gc, bg_nrec = synth.CONFIGS[args.workload + "_bg"]
+    if args.bg_bases:
+        n_bg = int(args.bg_bases)
+    words = int(lib.swga_tables_words(KMIN, KMAX))
+
+    class Dev(object):
+        """one genome (or one rank's shard of it) resident in HBM"""
+
+        def __init__(self, seed, n_total, gc, n_rec, shard):
+            rs = synth.equal_records(n_total, n_rec)
+            a, b = dist.shard_bounds(n_total, rank, world) if shard else (0, n_total)
+            e = min(n_total, b + KMAX - 1)
+            self.n, self.n_starts, self.a = e - a, b - a, a
+            self.mode_b = bool(np.diff(rs.astype(np.int64))[:10001].max() > 1000000)
+            inner = rs[(rs > a) & (rs < e)] - np.uint64(a)
+            self.rs = np.concatenate([[0], inner, [e - a]]).astype(np.uint64)
+            ta, tc, tg = synth.thresholds(gc)
+            self.ascii = torch.empty(max(self.n, 16), dtype=torch.uint8, device=dev)
+            _lib.check(lib.swga_synth_bases(ctx.h, seed, a, self.n, ta, tc, tg, P(self.ascii), None))
+            self.d_rs = torch.from_numpy(self.rs.view(np.int64).copy()).to(dev)
+            self.packed = torch.empty(int(lib.swga_packed_words(self.n)), dtype=torch.int32, device=dev)
+            self.brk = torch.empty(int(lib.swga_brk_words(self.n)), dtype=torch.int32, device=dev)
+            self.fwd = torch.empty(words, dtype=torch.int32, device=dev)
+            self.canon = torch.empty(words, dtype=torch.int32, device=dev)
+            self.launches = 0
+
+        def count(self, allreduce, ev=None):
+            self.fwd.zero_()
+            _lib.check(lib.swga_pack(ctx.h, P(self.ascii), self.n, 0 if self.mode_b else 1, P(self.packed), P(self.brk), None))
+            k = 1
+            if len(self.rs) > 2:
+                _lib.check(lib.swga_mark_records(ctx.h, P(self.d_rs[1:]), len(self.rs) - 2, self.n, P(self.brk), None))
+                k += 1
+            if ev is not None:
+                ev[0].record()
+            _lib.check(lib.swga_count_accumulate(ctx.h, P(self.packed), P(self.brk), self.n_starts, KMIN, KMAX, P(self.fwd), None))
+            if ev is not None:
+                ev[1].record()
+            if allreduce and world > 1:
+                td.all_reduce(self.fwd, op=td.ReduceOp.SUM)
+            _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
+            _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
+            self.launches = k + 1 + (KMAX - KMIN) + 1
+
+    fg = Dev(fg_seed, n_fg, fg_gc, fg_nrec, shard=False)
+    bg = Dev(bg_seed, n_bg, bg_gc, bg_nrec, shard=True)
+    torch.cuda.synchronize()
+
+    def step(ev=None):
+        fg.count(allreduce=False)
+        bg.count(allreduce=True, ev=ev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(kev[i])
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = e0.elapsed_time(e1)
+    count_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    t = torch.tensor([total_ms, count_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    total_ms, count_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = (n_fg + n_bg) / (ms_per_step * 1e-3) / 1e9
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+
+    # ---- roofline of the dominant kernel, k_count on this rank's background shard ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    count_bytes = 0.25 * bg.n_starts + 4.0 * 4 ** KMAX          # packed genome read once + top table written once
+    achieved = count_bytes / (count_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k_count_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = tr["dram_bytes_per_base"] * bg.n_starts
+    except Exception:
+        pass
+    roofline = {"kernel": "k_count", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "ms_per_launch": count_ms, "share_of_step": count_ms / ms_per_step,
+                "note": "k_count is bound by L2 red.global throughput, not HBM: see 'atomic'"}
+    path_bytes = 1.5 * (fg.n + bg.n) + 2 * 2 * 4.0 * words       # 1.5 B/base + 2T per genome
+    path = {"bytes_alg": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s"}
+    path["frac"] = path["achieved"] / hbm_peak
+
+    # ---- A_peak: random red.global.add.u32 on a 64 MB table; shared atomics on a 64 KB table ----
+    atomic = None
+    if rank == 0 and not args.no_extras:
+        ms = ctypes.c_float()
+        tab = torch.zeros(1 << 24, dtype=torch.int32, device=dev)
+        _lib.check(lib.swga_bench_red_global(ctx.h, P(tab), 1 << 24, 1 << 31, ctypes.byref(ms)))
+        red_peak = (1 << 31) / (ms.value * 1e-3) / 1e9
+        _lib.check(lib.swga_bench_atom_shared(ctx.h, 1 << 14, 1 << 33, ctypes.byref(ms)))
+        sh_peak = (1 << 33) / (ms.value * 1e-3) / 1e9
+        ach = bg.n_starts / (count_ms * 1e-3) / 1e9
+        atomic = {"achieved_gops": ach, "red_global_64MB_peak_gops": red_peak, "frac": ach / red_peak,
+                  "atom_shared_64KB_peak_gops": sh_peak, "ops_alg_per_base": 1,
+                  "note": "1 red per base (top table k=12 + tails); k<12 by marginalisation"}
+        del tab
+
+    # ---- e2e: host buffers through the C-ABI host calls, H2D + D2H inside the timed region ------
+    e2e = None
+    if not args.no_e2e:
+        h_fg = torch.empty(fg.n, dtype=torch.uint8, pin_memory=True)
+        h_bg = torch.empty(bg.n, dtype=torch.uint8, pin_memory=True)
+        h_fg.copy_(fg.ascii[:fg.n])
+        h_bg.copy_(bg.ascii[:bg.n])
+        h_canon_fg = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        h_canon_bg = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        cs = torch.cuda.ExternalStream(lib.swga_ctx_compute_stream(ctx.h), device=dev)
+        fg_rs, bg_rs = np.ascontiguousarray(fg.rs), np.ascontiguousarray(bg.rs)
+
+        def e2e_step():
+            _lib.check(lib.swga_count_genome_host(ctx.h, P(h_fg), fg.n, P(fg_rs), len(fg_rs) - 1, int(fg.mode_b),
+                                                  KMIN, KMAX, P(h_canon_fg)))
+            with torch.cuda.stream(cs):
+                bg.fwd.zero_()
+                _lib.check(lib.swga_count_stream_host(ctx.h, P(h_bg), bg.n, P(bg_rs), len(bg_rs) - 1, int(bg.mode_b),
+                                                      KMIN, KMAX, bg.n_starts, P(bg.fwd)))
+                if world > 1:
+                    td.all_reduce(bg.fwd, op=td.ReduceOp.SUM)
+                _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(bg.fwd), cs.cuda_stream))
+                _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(bg.fwd), P(bg.canon), cs.cuda_stream))
+                h_canon_bg.copy_(bg.canon, non_blocking=True)
+            cs.synchronize()
+
+        n_e2e = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(dt, op=td.ReduceOp.MAX)
+        e2e = {"value": (n_fg + n_bg) / float(dt[0]) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(fg.n + bg.n + 8 * (len(fg_rs) + len(bg_rs))),
+               "d2h_bytes_per_step": int(2 * 4 * words), "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
+               "api": "swga_count_genome_host / swga_count_stream_host (pinned host buffers)"}
+        # parity of the two paths on the full-size workload: a checksum of the tables
+        same = bool(torch.equal(h_canon_bg.to(dev), bg.canon))
+        e2e["tables_equal_device_path"] = same
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        dt, bases, kind, cores = cpu_reference_pass(args.workload, args.cpu_sample_bases, 1)
+        cpu = {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d-base prefix of the background: dsk k=5..12 run one after another (as "
+                         "swga/commands/count.py:84-91 does) + record parser; %.1f s" % (bases, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "fg_bases": n_fg, "bg_bases": n_bg,
+                       "kmin": KMIN, "kmax": KMAX, "sharding": "bg contiguous chunks + 11-base halo, fg replicated"
+                       if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
+            "roofline": roofline, "path_roofline": path, "atomic": atomic, "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

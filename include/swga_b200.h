@@ -137,6 +137,15 @@ int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n,
                            const uint64_t *h_rec_starts, uint64_t n_rec, int mode_b,
                            int kmin, int kmax, uint32_t *h_canon);
 
+/* The streaming half of swga_count_genome_host for multi-GPU hosts: accumulates the additive form of
+ * the owned starts [0, n_starts) of this rank's slice (h_seq holds n >= n_starts bases: the slice
+ * plus its right halo) into the caller-zeroed device block d_fwd, asynchronously on the context's
+ * compute stream (swga_ctx_compute_stream); the caller then allreduces, finalizes and folds. */
+int   swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n,
+                             const uint64_t *h_rec_starts, uint64_t n_rec, int mode_b,
+                             int kmin, int kmax, uint64_t n_starts, uint32_t *d_fwd);
+void *swga_ctx_compute_stream(swga_ctx *ctx);
+
 /* DSK result-file writer (ext/dsk/minia/SortingCount.cpp:149-156,649-653; read back by
  * swga/kmers.py:94-115): [i32 64][i32 k] then (u64 code, u32 count) for every count >= threshold. */
 int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,

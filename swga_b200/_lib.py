@@ -48,6 +48,9 @@ SIGNATURES = {
                                                 c_vp, c_vp, c_vp]),
     "swga_count_genome_host": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, c_vp]),
+    "swga_count_stream_host": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_vp]),
+    "swga_ctx_compute_stream": (c_vp, [c_ctx]),
     "swga_write_dsk_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, c_vp, ctypes.c_uint32, c_u64p]),
     "swga_synth_bases": (ctypes.c_int, [c_ctx, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),

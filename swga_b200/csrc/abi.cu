@@ -256,21 +256,20 @@ extern "C" int swga_count_genome_device(swga_ctx *ctx, const uint8_t *d_ascii, u
 // ---- whole-genome counting, host buffers (what swga/kmers.py would call instead of `dsk`) -----
 // The genome is cut into chunks of CHUNK start positions; chunk i needs bases
 // [a_i, min(n, b_i + kmax - 1)).  H2D of chunk i+1 (stream s_copy) overlaps pack + count of chunk i
-// (stream s_comp) through two staging buffers.
-extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n, const uint64_t *h_rec_starts,
-                                      uint64_t n_rec, int mode_b, int kmin, int kmax, uint32_t *h_canon)
+// (stream s_comp) through two staging buffers.  Accumulates into d_fwd (additive form) on s_comp
+// and returns without synchronising s_comp.
+extern "C" int swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n, const uint64_t *h_rec_starts,
+                                      uint64_t n_rec, int mode_b, int kmin, int kmax, uint64_t n_starts,
+                                      uint32_t *d_fwd)
 {
-    ARG_CHECK(ctx && (h_seq || n == 0) && h_canon && (h_rec_starts || n_rec == 0));
+    ARG_CHECK(ctx && (h_seq || n == 0) && d_fwd && (h_rec_starts || n_rec == 0) && n_starts <= n);
     if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
         swga_set_error("need 2 <= kmin <= kmax <= %d", SWGA_KMAX_LIMIT);
         return SWGA_E_ARG;
     }
     CUDA_TRY(cudaSetDevice(ctx->device));
     const uint64_t CHUNK = 64ull << 20;                        // start positions per chunk (multiple of 32)
-    const uint64_t words = swga_tables_words(kmin, kmax);
     const int mask_mode = mode_b ? SWGA_MASK_NONE : SWGA_MASK_N;
-    TRY(swga_ensure(ctx, ctx->fwd, words * 4));
-    TRY(swga_ensure(ctx, ctx->canon, words * 4));
     const uint64_t cap = std::min<uint64_t>(n, CHUNK + 64);
     for (int i = 0; i < 2; ++i) {
         TRY(swga_ensure(ctx, ctx->ascii[i], cap + 64));
@@ -281,12 +280,10 @@ extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
         TRY(swga_ensure(ctx, ctx->recs, (n_rec + 1) * 8));
         CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, h_rec_starts, (n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->s_comp));
     }
-    uint32_t *fwd = (uint32_t *)ctx->fwd.p, *canon = (uint32_t *)ctx->canon.p;
-    CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
     int it = 0;
-    for (uint64_t a = 0; a < n; a += CHUNK, ++it) {
+    for (uint64_t a = 0; a < n_starts; a += CHUNK, ++it) {
         const int b = it & 1;
-        const uint64_t e_starts = std::min(n, a + CHUNK);      // owned starts [a, e_starts)
+        const uint64_t e_starts = std::min(n_starts, a + CHUNK);   // owned starts [a, e_starts)
         const uint64_t e_bases = std::min(n, e_starts + (uint64_t)kmax - 1);
         const uint64_t len = e_bases - a;
         if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));
@@ -303,9 +300,29 @@ extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
                 TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p + (lo - h_rec_starts),
                                              (uint64_t)(hi - lo), a, len, brk, ctx->s_comp));
         }
-        TRY(swga_count_accumulate(ctx, packed, brk, e_starts - a, kmin, kmax, fwd, ctx->s_comp));
+        TRY(swga_count_accumulate(ctx, packed, brk, e_starts - a, kmin, kmax, d_fwd, ctx->s_comp));
         CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
     }
+    return SWGA_OK;
+}
+
+extern "C" void *swga_ctx_compute_stream(swga_ctx *ctx) { return ctx ? (void *)ctx->s_comp : nullptr; }
+
+extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n, const uint64_t *h_rec_starts,
+                                      uint64_t n_rec, int mode_b, int kmin, int kmax, uint32_t *h_canon)
+{
+    ARG_CHECK(ctx && h_canon);
+    if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
+        swga_set_error("need 2 <= kmin <= kmax <= %d", SWGA_KMAX_LIMIT);
+        return SWGA_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t words = swga_tables_words(kmin, kmax);
+    TRY(swga_ensure(ctx, ctx->fwd, words * 4));
+    TRY(swga_ensure(ctx, ctx->canon, words * 4));
+    uint32_t *fwd = (uint32_t *)ctx->fwd.p, *canon = (uint32_t *)ctx->canon.p;
+    CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
+    TRY(swga_count_stream_host(ctx, h_seq, n, h_rec_starts, n_rec, mode_b, kmin, kmax, n, fwd));
     TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
     TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
     CUDA_TRY(cudaMemcpyAsync(h_canon, canon, words * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
