@@ -151,6 +151,61 @@ void *swga_ctx_compute_stream(swga_ctx *ctx);
 int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,
                         uint64_t *n_written);
 
+/* ---- kernel (c): CSR position index + locate ------------------------------------------------
+ * Replaces the per-primer str.find scans of swga/locate.py:39-51,76-90 with one index per k:
+ *   d_offsets   [swga_index_offsets_words(k)] exclusive scan of the per-code histogram; slot 4^k holds
+ *               *n_valid (start of the sentinel bucket of windows that can never match)
+ *   d_positions [n] (the first *n_valid are used) linearised start positions, ascending inside a code
+ * d_packed/d_brk come from swga_pack(..., SWGA_MASK_STRICT, ...) + swga_mark_records, so only windows
+ * of upper-case A/C/G/T inside one record are indexed (locate.py:83-86 matches raw bytes per record).
+ * Synchronises the stream (returns *n_valid). */
+uint64_t swga_index_offsets_words(int k);
+int swga_build_index(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n, int k,
+                     uint32_t *d_offsets, uint32_t *d_positions, uint64_t *n_valid, void *stream);
+/* O(1) locate: d_counts[i] = number of sites of code d_codes[i]; then gather each code's sites
+ * (ascending) to d_out + d_out_off[i].  binding_sites(kmer) = sites of code(kmer) followed by sites of
+ * code(revcomp(kmer)) (locate.py:45-47), split per record by the host. */
+int swga_locate_counts(swga_ctx *ctx, int k, const uint32_t *d_offsets, const uint32_t *d_codes, uint32_t q,
+                       uint32_t *d_counts, void *stream);
+int swga_locate_gather(swga_ctx *ctx, int k, const uint32_t *d_offsets, const uint32_t *d_positions,
+                       const uint32_t *d_codes, uint32_t q, const uint64_t *d_out_off, uint32_t *d_out,
+                       void *stream);
+/* Per primer p: sorted union of its forward hits d_hits[d_hit_off[2p] .. d_hit_off[2p+1]) and its
+ * reverse-complement hits [d_hit_off[2p+1] .. d_hit_off[2p+2]) into d_out + d_out_off[p].  The two are
+ * disjoint unless d_is_pal[p] (primer == its reverse complement: the lists are equal and the union is
+ * the forward list; locate.py:33's set() removes the duplicates the same way). */
+int swga_union_strands(swga_ctx *ctx, const uint32_t *d_hits, const uint64_t *d_hit_off,
+                       const uint8_t *d_is_pal, uint32_t n_primers, const uint64_t *d_out_off,
+                       uint32_t *d_out, void *stream);
+/* d_toff[l * (n_tiles+1) + t] = index into d_sites of the first site of list l that is >= t << tile_shift
+ * (d_site_off has n_lists + 1 entries).  The scoring kernel walks the genome in such tiles. */
+int swga_tile_offsets(swga_ctx *ctx, const uint32_t *d_sites, const uint64_t *d_site_off, uint32_t n_lists,
+                      int tile_shift, uint32_t n_tiles, uint32_t *d_toff, void *stream);
+
+/* ---- kernel (d): batched scoring of candidate primer sets ---------------------------------------
+ * Replaces score.score_set / default_score_set (swga/score.py:27-53,73-98) with
+ * locate.linearize_binding_sites (swga/locate.py:22-36) and stats.seq_diff/mean/stdev/gini
+ * (swga/stats.py:10-54) for S sets per launch.
+ *   d_sites / d_toff  site lists (sorted, unique, linearised) of every primer plus one extra list,
+ *                     id `bounds_list`, holding the first and last position of every record
+ *                     (locate.py:30-32 adds them for every primer); tile offsets from
+ *                     swga_tile_offsets with tile_shift = swga_score_tile_shift()
+ *   d_sets            [S][max_m] list ids, -1 padded
+ *   d_bg_dist_mean    [S] (set_finder's weight or score.calculate_bg_dist_mean)
+ * Outputs per set: n_sites (unique positions), max_dist, mean / stdev / gini of the gaps, the default
+ * score (mean*gini)/bg_dist_mean, status bit0 = passed (interactive or max_dist <= max_fg_bind_dist),
+ * bit1 = largest gap beyond the in-kernel histogram (gini is NaN: use swga_gini_unbounded). */
+uint32_t swga_score_tile_shift(void);
+uint32_t swga_score_max_hist_bins(void);
+int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,
+                    uint32_t bounds_list, const int32_t *d_sets, uint32_t S, uint32_t max_m,
+                    const double *d_bg_dist_mean, uint32_t max_fg_bind_dist, int interactive,
+                    uint32_t *d_n_sites, uint32_t *d_max_dist, double *d_mean, double *d_stdev,
+                    double *d_gini, double *d_score, uint8_t *d_status, void *stream);
+int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,
+                        uint32_t bounds_list, const int32_t *d_set, uint32_t max_m, uint64_t max_gaps,
+                        double *h_gini, void *stream);
+
 /* ---- synthetic genomes (SURVEY.md 8d generator, bit-identical to swga_b200/synth.py) ----------- */
 int swga_synth_bases(swga_ctx *ctx, uint64_t seed, uint64_t start, uint64_t n,
                      uint32_t t_a, uint32_t t_c, uint32_t t_g, uint8_t *d_ascii, void *stream);

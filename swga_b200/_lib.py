@@ -52,6 +52,19 @@ SIGNATURES = {
                                               ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_vp]),
     "swga_ctx_compute_stream": (c_vp, [c_ctx]),
     "swga_write_dsk_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, c_vp, ctypes.c_uint32, c_u64p]),
+    "swga_index_offsets_words": (ctypes.c_uint64, [ctypes.c_int]),
+    "swga_build_index": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint64, ctypes.c_int, c_vp, c_vp, c_u64p, c_vp]),
+    "swga_locate_counts": (ctypes.c_int, [c_ctx, ctypes.c_int, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp]),
+    "swga_locate_gather": (ctypes.c_int, [c_ctx, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    "swga_union_strands": (ctypes.c_int, [c_ctx, c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+    "swga_tile_offsets": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp]),
+    "swga_score_tile_shift": (ctypes.c_uint32, []),
+    "swga_score_max_hist_bins": (ctypes.c_uint32, []),
+    "swga_score_sets": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, ctypes.c_uint32,
+                                       ctypes.c_uint32, c_vp, ctypes.c_uint32, ctypes.c_int,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "swga_gini_unbounded": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, ctypes.c_uint32,
+                                           ctypes.c_uint64, c_f64p, c_vp]),
     "swga_synth_bases": (ctypes.c_int, [c_ctx, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
     "swga_bench_red_global": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_uint64,

@@ -69,7 +69,8 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_buf(c->packed); free_buf(c->brk); free_buf(c->fwd); free_buf(c->canon); free_buf(c->recs);
-    free_buf(c->scratch);
+    free_buf(c->scratch); free_buf(c->sort_hist); free_buf(c->score_tmp);
+    for (int i = 0; i < 2; ++i) { free_buf(c->sort_keys[i]); free_buf(c->sort_vals[i]); }
     for (int i = 0; i < 2; ++i) {
         free_buf(c->ascii[i]); free_buf(c->packed2[i]); free_buf(c->brk2[i]);
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);

@@ -47,6 +47,7 @@ struct swga_ctx {
     cudaStream_t s_copy = nullptr, s_comp = nullptr;   // used by the *_host pipelines
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf packed, brk, ascii[2], packed2[2], brk2[2], fwd, canon, recs, scratch;
+    DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp;
 };
 
 int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes);   // grow-only workspace

@@ -1,0 +1,386 @@
+// score.cu -- kernel (d): batched scoring of candidate primer sets.
+//
+// Results reproduced (reference = eclarke/swga), one set per CTA-iteration:
+//   swga/locate.py:22-36   linearize_binding_sites: union over the set's primers of their linearised
+//                          sites, plus the first and last position of every record, de-duplicated
+//   swga/stats.py:22-33    seq_diff: ascending sort, adjacent differences ("gaps")
+//   swga/score.py:83-90    max_dist = max(gaps); reject when max_dist > max_fg_bind_dist
+//   swga/stats.py:10-19    mean = float(sum)/n ; stdev = sqrt(sum((x-mu)^2)/(n-1))
+//   swga/stats.py:36-54    gini with Python-2 floor division in fair_area = height*n/2
+//   swga/commands/specfiles/find_sets.yaml:39-40  default score (fg_dist_mean*fg_dist_gini)/bg_dist_mean
+//
+// Method: the union is formed in a shared-memory bitmap, one coordinate tile of 2^19 positions at a
+// time.  Every site sets one bit (shared-memory atomicOr; a second-level bitmap marks non-empty
+// words), then each thread walks the set bits of its 1024-position slice in ascending order and
+// emits gaps; the gap to the previous slice / tile comes from a block-wide running maximum.  Gaps
+// feed exact integer accumulators (count, sum of squares, max) and a shared-memory value histogram
+// from which the rank-weighted sum that Gini needs is obtained without sorting.  All integer
+// statistics are exact; mean and Gini are bit-identical to the reference's floating point (one
+// rounding each); stdev differs only by summation order (~1e-15 relative).
+#include "common.cuh"
+
+#define SC_THREADS 512
+#define SC_WARPS (SC_THREADS / 32)
+#define SC_TILE_SHIFT 19                                   // 2^19 positions per tile = 1024 per thread
+#define SC_L0_WORDS ((1u << SC_TILE_SHIFT) / 32)           // 16384
+#define SC_L0_PHYS (SC_L0_WORDS + SC_L0_WORDS / 32)        // padded: phys(w) = w + (w >> 5)
+#define SC_L1_WORDS (SC_L0_WORDS / 32)                     // 512 == SC_THREADS
+#define SC_MAX_LISTS 32                                    // set members + the record-bounds list
+
+struct ScoreArgs {
+    const uint32_t *sites;       // concatenated sorted-unique site lists (linear coordinates)
+    const uint32_t *toff;        // [n_lists][n_tiles + 1] tile offsets into sites
+    uint32_t n_tiles;
+    uint32_t bounds_list;        // id of the list holding every record's first and last position
+    const int32_t *sets;         // [S][max_m] list ids, -1 padded
+    uint32_t S, max_m;
+    const double *bg_dist_mean;  // [S]
+    uint32_t max_fg_bind_dist;
+    uint32_t hist_bins;          // gaps < hist_bins are histogrammed (Gini); 0 disables
+    int interactive;             // score.py:89: never reject
+    // outputs, [S] each
+    uint32_t *n_sites, *max_dist;
+    double *mean, *stdev, *gini, *score;
+    uint8_t *status;             // bit0: passed the max_dist filter; bit1: Gini needs the unbounded path
+    // optional gap dump for the unbounded path (single set): gaps of set 0 are appended here
+    uint32_t *gap_out;
+    uint32_t *gap_count;
+};
+
+__device__ __forceinline__ uint32_t phys(uint32_t w) { return w + (w >> 5); }
+
+__device__ __forceinline__ uint32_t warp_incl_max(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) >= d) v = max(v, o);
+    }
+    return v;
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T *scratch /* SC_WARPS + 1 */)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T w = threadIdx.x < SC_WARPS ? scratch[threadIdx.x] : scratch[0];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, d));
+        if (threadIdx.x == 0) scratch[SC_WARPS] = w;
+    }
+    __syncthreads();
+    return scratch[SC_WARPS];
+}
+
+struct OpAddU32 { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a + b; } };
+struct OpAddU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
+struct OpMaxU32 { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return max(a, b); } };
+struct OpMinU32 { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return min(a, b); } };
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+k_score(ScoreArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t *L0 = smem;                                   // SC_L0_PHYS
+    uint32_t *L1 = L0 + SC_L0_PHYS;                        // SC_L1_WORDS
+    uint32_t *hist = L1 + SC_L1_WORDS;                     // a.hist_bins
+    __shared__ uint32_t s_lo[SC_MAX_LISTS], s_hi[SC_MAX_LISTS], s_list[SC_MAX_LISTS];
+    __shared__ uint32_t s_warp[SC_WARPS + 1];
+    __shared__ unsigned long long s_red64[SC_WARPS + 1];
+    __shared__ uint32_t s_red32[SC_WARPS + 1];
+    __shared__ uint32_t s_nlists;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < SC_L0_PHYS + SC_L1_WORDS + a.hist_bins; i += SC_THREADS) smem[i] = 0;
+    __syncthreads();
+
+    for (uint32_t s = blockIdx.x; s < a.S; s += gridDim.x) {
+        // ---- members of this set (+ the record-bounds list) ----
+        if (tid == 0) {
+            uint32_t n = 0;
+            for (uint32_t j = 0; j < a.max_m && n < SC_MAX_LISTS - 1; ++j) {
+                const int32_t id = a.sets[(uint64_t)s * a.max_m + j];
+                if (id >= 0) s_list[n++] = (uint32_t)id;
+            }
+            s_list[n++] = a.bounds_list;
+            s_nlists = n;
+        }
+        __syncthreads();
+        const uint32_t nl = s_nlists;
+
+        uint32_t cnt = 0, maxgap = 0, first = 0xffffffffu;
+        unsigned long long sumsq = 0;
+        uint32_t carry = 0;                                // (last position so far) + 1; 0 = none
+
+        for (uint32_t t = 0; t < a.n_tiles; ++t) {
+            if (tid < nl) {
+                const uint32_t *row = a.toff + (uint64_t)s_list[tid] * (a.n_tiles + 1) + t;
+                s_lo[tid] = row[0];
+                s_hi[tid] = row[1];
+            }
+            __syncthreads();
+            uint32_t total = 0;
+            for (uint32_t l = 0; l < nl; ++l) total += s_hi[l] - s_lo[l];
+            if (total == 0) { __syncthreads(); continue; }   // uniform: nothing in this tile
+            const uint32_t tile_base = t << SC_TILE_SHIFT;
+            // ---- fill: one bit per site ----
+            for (uint32_t l = 0; l < nl; ++l) {
+                const uint32_t hi = s_hi[l];
+                for (uint32_t i = s_lo[l] + tid; i < hi; i += SC_THREADS) {
+                    const uint32_t p = a.sites[i] - tile_base;
+                    const uint32_t w = p >> 5;
+                    const uint32_t old = atomicOr(&L0[phys(w)], 1u << (p & 31));
+                    if (old == 0) atomicOr(&L1[w >> 5], 1u << (w & 31));
+                }
+            }
+            __syncthreads();
+            // ---- scan: thread owns L1 word `tid` = L0 words [32 tid, 32 tid + 32) ----
+            uint32_t m1 = L1[tid];
+            L1[tid] = 0;
+            uint32_t enc = 0;                              // (last position in my slice) + 1
+            if (m1) {
+                const uint32_t j = 31 - __clz(m1);
+                const uint32_t w = L0[phys(32 * tid + j)];
+                enc = tile_base + (((32 * tid + j) << 5) | (31 - __clz(w))) + 1;
+            }
+            // exclusive running max over threads, seeded with the carry from earlier tiles
+            uint32_t inc = warp_incl_max(enc);
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = lane < SC_WARPS ? s_warp[lane] : 0;
+                uint32_t vi = warp_incl_max(v);
+                uint32_t ve = __shfl_up_sync(0xffffffffu, vi, 1);
+                if (lane == 0) ve = 0;
+                if (lane < SC_WARPS) s_warp[lane] = ve;
+                if (lane == 31) s_warp[SC_WARPS] = vi;     // max over the whole tile
+            }
+            __syncthreads();
+            uint32_t pred = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) pred = 0;
+            pred = max(max(pred, s_warp[warp]), carry);
+            carry = max(carry, s_warp[SC_WARPS]);
+            // ---- enumerate my set bits in ascending order ----
+            while (m1) {
+                const uint32_t j = __ffs(m1) - 1;
+                m1 &= m1 - 1;
+                const uint32_t pw = phys(32 * tid + j);
+                uint32_t w = L0[pw];
+                L0[pw] = 0;
+                const uint32_t wbase = tile_base + ((32 * tid + j) << 5);
+                while (w) {
+                    const uint32_t pos = wbase + (__ffs(w) - 1);
+                    w &= w - 1;
+                    if (pred) {
+                        const uint32_t gap = pos - (pred - 1);
+                        ++cnt;
+                        sumsq += (unsigned long long)gap * gap;
+                        maxgap = max(maxgap, gap);
+                        if (gap < a.hist_bins) atomicAdd(&hist[gap], 1u);
+                        if (a.gap_out && s == 0) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
+                    } else {
+                        first = pos;
+                    }
+                    pred = pos + 1;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- reduce over the block ----
+        const uint32_t n = block_reduce(cnt, OpAddU32(), s_red32);            // number of gaps
+        const uint32_t mx = block_reduce(maxgap, OpMaxU32(), s_red32);
+        const uint32_t fst = block_reduce(first, OpMinU32(), s_red32);
+        const unsigned long long ssq = block_reduce(sumsq, OpAddU64(), s_red64);
+        const uint32_t last = carry ? carry - 1 : 0;
+        const unsigned long long H = (carry && fst != 0xffffffffu) ? (unsigned long long)(last - fst) : 0ull;
+
+        const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
+        const bool hist_ok = mx < a.hist_bins;
+        // ---- rank-weighted sum from the histogram (and clear it) ----
+        unsigned long long sum_prefix = 0;
+        if (a.hist_bins) {
+            const uint32_t top = min(mx, a.hist_bins - 1);                    // highest bin that can be non-zero
+            const uint32_t per = top / SC_THREADS + 1;
+            const uint32_t b0 = tid * per, b1 = min(b0 + per, top + 1);
+            uint32_t c_mine = 0;
+            for (uint32_t v = b0; v < b1; ++v) c_mine += hist[v];
+            // exclusive scan of c_mine over threads
+            uint32_t inc = c_mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (uint32_t)d) inc += o;
+            }
+            __syncthreads();
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = lane < SC_WARPS ? s_warp[lane] : 0, vi = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(0xffffffffu, vi, d);
+                    if (lane >= (uint32_t)d) vi += o;
+                }
+                if (lane < SC_WARPS) s_warp[lane] = vi - v;
+            }
+            __syncthreads();
+            unsigned long long r = s_warp[warp] + inc - c_mine;               // gaps smaller than my first bin
+            unsigned long long part = 0;
+            for (uint32_t v = b0; v < b1; ++v) {
+                const unsigned long long c = hist[v];
+                hist[v] = 0;
+                if (c) {
+                    // ranks r+1 .. r+c (ascending): sum of (n - rank + 1) = c (n - r) - c (c - 1) / 2
+                    part += (unsigned long long)v * (c * ((unsigned long long)n - r) - c * (c - 1) / 2);
+                    r += c;
+                }
+            }
+            sum_prefix = block_reduce(part, OpAddU64(), s_red64);
+        }
+
+        if (tid == 0) {
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            double mean = nan, sd = nan, gini = nan, score = nan;
+            if (n > 0) {
+                mean = (double)H / (double)n;                                  // stats.py:12
+                if (n > 1) {
+                    const unsigned __int128 num = (unsigned __int128)n * ssq - (unsigned __int128)H * H;
+                    sd = sqrt((double)num / ((double)n * (double)(n - 1)));    // stats.py:17-19
+                }
+                if (a.hist_bins && hist_ok) {
+                    const unsigned long long fair = (H * (unsigned long long)n) / 2;   // Python-2 floor, stats.py:53
+                    if (fair > 0) {
+                        const long long two_area = (long long)(2 * sum_prefix) - (long long)H;
+                        gini = (double)((long long)(2 * fair) - two_area) / (double)(2 * fair);
+                    }
+                }
+                score = (mean * gini) / a.bg_dist_mean[s];
+            }
+            a.n_sites[s] = carry ? n + 1 : 0;
+            a.max_dist[s] = mx;
+            a.mean[s] = mean;
+            a.stdev[s] = sd;
+            a.gini[s] = gini;
+            a.score[s] = score;
+            a.status[s] = (uint8_t)((passed ? 1 : 0) | ((!hist_ok) ? 2 : 0));
+        }
+        __syncthreads();
+    }
+}
+
+// Gini of an ascending-sorted gap array (the unbounded path, one set): sum_prefix by a block reduction
+__global__ void __launch_bounds__(SC_THREADS)
+k_gini_sorted(const uint32_t *__restrict__ gaps, uint32_t n, double *__restrict__ out)
+{
+    __shared__ unsigned long long s_red64[SC_WARPS + 1];
+    unsigned long long part = 0, h = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += SC_THREADS) {
+        part += (unsigned long long)gaps[i] * (n - i);                        // rank i+1 ascending: n - rank + 1
+        h += gaps[i];
+    }
+    const unsigned long long sum_prefix = block_reduce(part, OpAddU64(), s_red64);
+    const unsigned long long H = block_reduce(h, OpAddU64(), s_red64);
+    if (threadIdx.x == 0) {
+        double gini = __longlong_as_double(0x7ff8000000000000ll);
+        const unsigned long long fair = (H * (unsigned long long)n) / 2;
+        if (fair > 0) {
+            const long long two_area = (long long)(2 * sum_prefix) - (long long)H;
+            gini = (double)((long long)(2 * fair) - two_area) / (double)(2 * fair);
+        }
+        *out = gini;
+    }
+}
+
+int swga_radix_sort_pairs(swga_ctx *ctx, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
+                          uint64_t n, int bits, bool vals_are_index, int *result_in_a, cudaStream_t stream);
+
+extern "C" uint32_t swga_score_tile_shift(void) { return SC_TILE_SHIFT; }
+extern "C" uint32_t swga_score_max_hist_bins(void)
+{
+    return (227u * 1024u - 4u * (SC_L0_PHYS + SC_L1_WORDS) - 2048u) / 4u;
+}
+
+extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,
+                               uint32_t bounds_list, const int32_t *d_sets, uint32_t S, uint32_t max_m,
+                               const double *d_bg_dist_mean, uint32_t max_fg_bind_dist, int interactive,
+                               uint32_t *d_n_sites, uint32_t *d_max_dist, double *d_mean, double *d_stdev,
+                               double *d_gini, double *d_score, uint8_t *d_status, void *stream)
+{
+    ARG_CHECK(ctx && d_toff && n_tiles > 0);
+    if (S == 0) return SWGA_OK;
+    ARG_CHECK(d_sets && d_bg_dist_mean && d_n_sites && d_max_dist && d_mean && d_stdev && d_gini && d_score && d_status);
+    ARG_CHECK(max_m + 1 <= SC_MAX_LISTS);
+    ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sites = d_sites; a.toff = d_toff; a.n_tiles = n_tiles; a.bounds_list = bounds_list;
+    a.sets = d_sets; a.S = S; a.max_m = max_m; a.bg_dist_mean = d_bg_dist_mean;
+    a.max_fg_bind_dist = max_fg_bind_dist; a.interactive = interactive;
+    const uint32_t cap = swga_score_max_hist_bins();
+    // gaps up to max_fg_bind_dist can occur in a passing set; when that does not fit, sets whose largest
+    // gap is >= cap are flagged (status bit1) for swga_gini_unbounded
+    uint64_t want = interactive ? cap : (uint64_t)max_fg_bind_dist + 1;
+    a.hist_bins = (uint32_t)(want < cap ? want : cap);
+    a.n_sites = d_n_sites; a.max_dist = d_max_dist; a.mean = d_mean; a.stdev = d_stdev; a.gini = d_gini;
+    a.score = d_score; a.status = d_status;
+    const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS + a.hist_bins);
+    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = S < (uint32_t)ctx->sm_count ? S : (uint32_t)ctx->sm_count;
+    k_score<<<grid, SC_THREADS, smem, as_stream(stream)>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}
+
+// Gini of ONE set without a bound on the gap size (interactive `swga score`, or max_fg_bind_dist beyond
+// the histogram capacity): dump the gaps, radix-sort them, rank-weighted sum.  Synchronises.
+extern "C" int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,
+                                   uint32_t bounds_list, const int32_t *d_set, uint32_t max_m, uint64_t max_gaps,
+                                   double *h_gini, void *stream_)
+{
+    ARG_CHECK(ctx && d_toff && d_set && h_gini && n_tiles > 0 && max_m + 1 <= SC_MAX_LISTS);
+    cudaStream_t stream = as_stream(stream_);
+    const size_t n = max_gaps ? max_gaps : 1;
+    TRY(swga_ensure(ctx, ctx->sort_keys[0], n * 4));
+    TRY(swga_ensure(ctx, ctx->sort_keys[1], n * 4));
+    TRY(swga_ensure(ctx, ctx->sort_vals[0], n * 4));
+    TRY(swga_ensure(ctx, ctx->sort_vals[1], n * 4));
+    TRY(swga_ensure(ctx, ctx->score_tmp, 256));
+    uint8_t *tmp = (uint8_t *)ctx->score_tmp.p;               // [0,8) bg  [8,16) gini  [16,20) gap_count, then outputs
+    CUDA_TRY(cudaMemsetAsync(tmp, 0, 256, stream));
+    ScoreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sites = d_sites; a.toff = d_toff; a.n_tiles = n_tiles; a.bounds_list = bounds_list;
+    a.sets = d_set; a.S = 1; a.max_m = max_m; a.bg_dist_mean = (const double *)tmp;
+    a.max_fg_bind_dist = 0xffffffffu; a.interactive = 1; a.hist_bins = 0;
+    a.n_sites = (uint32_t *)(tmp + 32); a.max_dist = (uint32_t *)(tmp + 40); a.mean = (double *)(tmp + 48);
+    a.stdev = (double *)(tmp + 56); a.gini = (double *)(tmp + 64); a.score = (double *)(tmp + 72);
+    a.status = tmp + 80;
+    a.gap_out = (uint32_t *)ctx->sort_keys[0].p;
+    a.gap_count = (uint32_t *)(tmp + 16);
+    const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS);
+    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    k_score<<<1, SC_THREADS, smem, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    uint32_t ng = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ng, tmp + 16, 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (ng > max_gaps) {
+        swga_set_error("gap buffer too small: %u gaps > %llu", ng, (unsigned long long)max_gaps);
+        return SWGA_E_OVERFLOW;
+    }
+    int in_a = 1;
+    TRY(swga_radix_sort_pairs(ctx, (uint32_t *)ctx->sort_keys[0].p, (uint32_t *)ctx->sort_vals[0].p,
+                              (uint32_t *)ctx->sort_keys[1].p, (uint32_t *)ctx->sort_vals[1].p, ng, 32, true, &in_a,
+                              stream));
+    k_gini_sorted<<<1, SC_THREADS, 0, stream>>>((const uint32_t *)ctx->sort_keys[in_a ? 0 : 1].p, ng,
+                                                (double *)(tmp + 8));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_gini, tmp + 8, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return SWGA_OK;
+}

@@ -1,0 +1,221 @@
+"""GPU parity for kernels (c) locate and (d) batched set scoring, through the C ABI, against the
+Python restatement of swga/locate.py, swga/stats.py and swga/score.py, plus the reference's own
+known-answer tests (swga/tests/test_locate.py, test_score.py, test_swga.py:132-154)."""
+import functools
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TEST_FASTA = b"> record1\nAAGGAAGGCCTTCCTT\n> record2\nAAAATTTT\n> record3\nAAGGCCTT"
+
+
+class P(object):
+    def __init__(self, locations, bg_freq=1):
+        self.locations, self.bg_freq = locations, bg_freq
+
+
+@pytest.fixture(scope="module")
+def quirky():
+    """3.2 Mbp, 5 records (one empty, one shorter than any primer), AT-rich, with lower-case, N and
+    IUPAC stretches that counting aliases to bases but locate must never match."""
+    from swga_b200 import fasta, synth
+    n = 3_200_000
+    seq = synth.bases(21, 0, n, 0.30)
+    seq[5000:5400] |= 0x20
+    seq[700_000:700_050] = ord("N")
+    seq[1_234_567] = ord("R")
+    seq[2_000_000:2_000_003] = ord("n")
+    rs = np.array([0, 1_000_003, 1_000_003, 1_000_009, 2_500_000, n], dtype=np.uint64)
+    names = ["chrA", "empty", "six", "chrB", "chrC"]
+    return fasta.Genome(seq, rs, names)
+
+
+def records_of(g):
+    s = g.seq.tobytes().decode("latin-1")
+    return [(g.names[r], s[int(g.rec_starts[r]):int(g.rec_starts[r + 1])]) for r in range(g.n_records)]
+
+
+def pick_primers(g, oracle, ks=(5, 6, 8, 10, 12), per_k=6, seed=3):
+    rng = np.random.RandomState(seed)
+    out = []
+    s = g.seq
+    for k in ks:
+        got = 0
+        while got < per_k:
+            p = int(rng.randint(0, g.n_bases - k))
+            w = s[p:p + k].tobytes().decode("latin-1")
+            if all(c in "ACGT" for c in w):
+                out.append(w)
+                got += 1
+    out += ["AATT", "ACGT", "AAAATTTT", "ATATATATAT", "GGGGGGGGGGGG"]      # palindromes and a rare one
+    return out
+
+
+def test_reference_locate_kats(oracle, tmp_path):
+    from swga_b200 import locate
+    fp = tmp_path / "test.fasta"
+    fp.write_bytes(TEST_FASTA)
+    loc = locate.binding_sites("AAGG", str(fp))
+    assert len(loc["record1"]) == 4 and loc["record2"] == []                 # test_locate.py:12-15
+    assert loc == oracle.binding_sites("AAGG", oracle.fasta_records_pyfaidx(TEST_FASTA))
+    ends = locate.chromosome_ends(str(fp))
+    assert ends == {"record1": [0, 15], "record2": [16, 23], "record3": [24, 31]}
+    lin = locate.linearize_binding_sites([P(loc)], ends)
+    assert len(lin) == 10
+    assert locate.revcomp("GCAT") == "ATGC"
+    with pytest.raises(KeyError):
+        locate.binding_sites("AANG", str(fp))
+    with pytest.raises(KeyError):
+        locate.binding_sites("aagg", str(fp))                                # revcomp() of lower case
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    with pytest.raises(ValueError):
+        locate.binding_sites("AAGG", str(empty))
+
+
+def test_palindrome_sites_listed_twice(oracle, tmp_path):
+    from swga_b200 import locate
+    fa = b">simple_genome\n" + b"\n".join([b"AAAATTTT" * 8] * 9) + b"\n"
+    fp = tmp_path / "simple.fa"
+    fp.write_bytes(fa)
+    loc = locate.binding_sites("AAAATTTT", str(fp))
+    assert loc == oracle.binding_sites("AAAATTTT", oracle.fasta_records_pyfaidx(fa))
+    assert len(loc["simple_genome"]) == 144 and loc["simple_genome"][:2] == [0, 8]
+
+
+def test_binding_sites_match_oracle_on_quirky_genome(quirky, oracle):
+    from swga_b200 import locate
+    gi = locate.GenomeIndex(quirky)
+    recs = records_of(quirky)
+    for primer in pick_primers(quirky, oracle):
+        got = gi.binding_sites(primer)
+        want = oracle.binding_sites(primer, recs)
+        assert list(got.keys()) == [n for n, _ in recs]
+        assert got == want, primer
+
+
+def test_locate_agrees_with_counts_on_clean_genome(oracle):
+    """on upper-case ACGT, sum over records of len(binding_sites(p)) == fg_freq(p) for
+    non-palindromic primers -- kernels (b) and (c) cross-checked."""
+    from swga_b200 import fasta, kmers, locate, synth
+    n = 1_500_000
+    g = fasta.Genome(synth.bases(31, 0, n, 0.5), np.array([0, 400_000, n], dtype=np.uint64), ["a", "b"])
+    tabs = kmers.count_all(g, 5, 12)
+    gi = locate.GenomeIndex(g)
+    for primer in pick_primers(g, oracle, per_k=4, seed=9)[:-5]:
+        k = len(primer)
+        f, r = kmers.kmer_to_code(primer), kmers.kmer_to_code(locate.revcomp(primer))
+        if f == r:
+            continue
+        sites = gi.binding_sites(primer)
+        assert sum(len(v) for v in sites.values()) == int(tabs.table(k)[min(f, r)])
+
+
+def _oracle_scores(oracle, locs_of, chr_ends, sets, bgs, max_fg, interactive):
+    out = []
+    for ids, bg in zip(sets, bgs):
+        pl = [locs_of[i] for i in ids if i >= 0]
+        out.append(oracle.score_set(pl, max_fg, bg, chr_ends, interactive=interactive))
+    return out
+
+
+def _check(res, i, want, bg):
+    score, var, max_dist = want
+    assert int(res.fg_max_dist[i]) == max_dist
+    if score is False:
+        assert not res.passed[i]
+        return
+    assert res.passed[i]
+    assert res.fg_dist_mean[i] == var["fg_dist_mean"]                        # bit-exact (one rounding)
+    assert res.fg_dist_gini[i] == var["fg_dist_gini"]                        # bit-exact
+    assert res.fg_dist_std[i] == pytest.approx(var["fg_dist_std"], rel=1e-9) # north_star: <= 1e-6 relative
+    assert res.score[i] == pytest.approx(score, rel=1e-12)
+
+
+def test_batched_scoring_matches_oracle(quirky, oracle):
+    from swga_b200 import locate, score
+    gi = locate.GenomeIndex(quirky)
+    recs = records_of(quirky)
+    primers = pick_primers(quirky, oracle)
+    locs_of = [oracle.binding_sites(p, recs) for p in primers]
+    chr_ends = oracle.chromosome_ends(recs)
+    assert gi.chromosome_ends() == chr_ends
+    sl = score.SiteLists.from_index(gi, primers)
+    # per-primer unique site counts agree with the oracle's linearisation
+    for i, p in enumerate(primers):
+        lin = set()
+        for rec, ls in locs_of[i].items():
+            lin.update(l + chr_ends[rec][0] for l in ls)
+        assert sl.counts()[sl.list_of_primer[i]] == len(lin), p
+    rng = np.random.RandomState(5)
+    S, max_m = 60, 10
+    sets = np.full((S, max_m), -1, dtype=np.int32)
+    for s in range(S):
+        m = rng.randint(1, max_m + 1)
+        sets[s, :m] = rng.choice(len(primers), m, replace=False)
+    sets[0, :] = -1
+    sets[0, 0] = len(primers) - 1                                            # a set of one rare primer
+    bgs = rng.uniform(100, 1e5, S)
+    bgs[1] = float("inf")
+    for max_fg, interactive in ((36000, False), (3000, False), (0, True)):
+        res = score.score_sets(sl, sets, bgs, max_fg, interactive=interactive)
+        want = _oracle_scores(oracle, locs_of, chr_ends, sets, bgs, max_fg, interactive)
+        n_pass = 0
+        for i in range(S):
+            _check(res, i, want[i], bgs[i])
+            n_pass += bool(res.passed[i])
+        assert n_pass > 0
+    # interactive sets include gaps far beyond the in-kernel histogram: the sort path was exercised
+    res = score.score_sets(sl, sets, bgs, 0, interactive=True)
+    assert ((res.status & 2) != 0).any()
+
+
+def test_reference_score_kats(oracle):
+    from swga_b200 import score
+    assert score.read_set_finder_line("1,2,3,4 3500.01234") == ([1, 2, 3, 4], 3500.01234)
+    s, ns = score.default_score_set("fg_dist_mean/bg_dist_mean", [1, 2, 3, 4], [1, 3, 5, 7], 2, 3.0)
+    assert s == 2.0 / 3.0 and "__builtins__" not in ns                       # test_score.py:18-29
+    with pytest.raises(NameError):
+        score.default_score_set("fg_dist_max", [1], [1, 3, 5, 7], 2, 3.0)
+    # SURVEY.md App. B3
+    fa = b">simple_genome\n" + b"\n".join([b"AAAATTTT" * 8] * 9) + b"\n"
+    recs = oracle.fasta_records_pyfaidx(fa)
+    loc = oracle.binding_sites("AAAATTTT", recs)
+    ends = oracle.chromosome_ends(recs)
+    fun = functools.partial(score.default_score_set, expression=score.DEFAULT_EXPRESSION)
+    sc, var, max_dist = score.score_set([P(loc, 0)], 36000, float("inf"), ends, fun)
+    assert (sc, max_dist) == (0.0, 8)
+    assert var["fg_dist_mean"] == 7.986111111111111 and var["fg_dist_gini"] == 0.001714975845410628
+    assert var["fg_dist_std"] == pytest.approx(0.11785113019775792, rel=1e-12)
+    assert var["set_size"] == 1 and var["fg_max_dist"] == 8 and set(var) == set(score.VARIABLES)
+    assert score.score_set([P(loc, 0)], 7, 1.0, ends, fun) == (False, {}, 8)
+    assert score.score_set([P(loc, 0)], 7, 1.0, ends, fun, interactive=True)[2] == 8
+    assert score.calculate_bg_dist_mean([P(loc, 2), P(loc, 3)], 10) == 2.0
+    assert score.calculate_bg_dist_mean([P(loc, 0)], 10) == float("inf")
+    # gini's Python-2 floor: gaps [1,1,1] -> -0.125
+    _, ns = score.default_score_set("fg_dist_gini", [1], [10, 11, 12, 13], 1, 1.0)
+    assert ns["fg_dist_gini"] == -0.125
+
+
+def test_set_index_sharding_needs_no_collective(quirky, oracle):
+    from swga_b200 import locate, score
+    gi = locate.GenomeIndex(quirky)
+    primers = pick_primers(quirky, oracle, per_k=3, seed=11)
+    sl = score.SiteLists.from_index(gi, primers)
+    rng = np.random.RandomState(2)
+    S = 37
+    sets = np.stack([rng.choice(len(primers), 6, replace=False) for _ in range(S)]).astype(np.int32)
+    bgs = rng.uniform(1e3, 1e4, S)
+    whole = score.score_sets(sl, sets, bgs, 36000)
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            lo, hi = score.shard_sets(S, rank, world)
+            if hi > lo:
+                parts.append(score.score_sets(sl, sets[lo:hi], bgs[lo:hi], 36000))
+        for key in ("fg_max_dist", "n_sites", "fg_dist_mean", "fg_dist_gini", "score"):
+            cat = np.concatenate([p[key] for p in parts])
+            assert np.array_equal(cat, whole[key], equal_nan=True), (world, key)
