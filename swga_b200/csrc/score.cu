@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t warp_incl_max(uint32_t v)
 }
 
 template <typename T, typename Op>
-__device__ __forceinline__ T block_reduce(T v, Op op, T *scratch /* SC_WARPS + 1 */)
+__device__ __forceinline__ T block_reduce(T v, Op op, T ident, T *scratch /* SC_WARPS + 1 */)
 {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
@@ -68,7 +68,7 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T *scratch /* SC_WARPS + 1
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x < 32) {
-        T w = threadIdx.x < SC_WARPS ? scratch[threadIdx.x] : scratch[0];
+        T w = threadIdx.x < SC_WARPS ? scratch[threadIdx.x] : ident;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, d));
         if (threadIdx.x == 0) scratch[SC_WARPS] = w;
@@ -193,10 +193,10 @@ k_score(ScoreArgs a)
         }
 
         // ---- reduce over the block ----
-        const uint32_t n = block_reduce(cnt, OpAddU32(), s_red32);            // number of gaps
-        const uint32_t mx = block_reduce(maxgap, OpMaxU32(), s_red32);
-        const uint32_t fst = block_reduce(first, OpMinU32(), s_red32);
-        const unsigned long long ssq = block_reduce(sumsq, OpAddU64(), s_red64);
+        const uint32_t n = block_reduce(cnt, OpAddU32(), 0u, s_red32);            // number of gaps
+        const uint32_t mx = block_reduce(maxgap, OpMaxU32(), 0u, s_red32);
+        const uint32_t fst = block_reduce(first, OpMinU32(), 0xffffffffu, s_red32);
+        const unsigned long long ssq = block_reduce(sumsq, OpAddU64(), 0ull, s_red64);
         const uint32_t last = carry ? carry - 1 : 0;
         const unsigned long long H = (carry && fst != 0xffffffffu) ? (unsigned long long)(last - fst) : 0ull;
 
@@ -241,7 +241,7 @@ k_score(ScoreArgs a)
                     r += c;
                 }
             }
-            sum_prefix = block_reduce(part, OpAddU64(), s_red64);
+            sum_prefix = block_reduce(part, OpAddU64(), 0ull, s_red64);
         }
 
         if (tid == 0) {
@@ -250,8 +250,12 @@ k_score(ScoreArgs a)
             if (n > 0) {
                 mean = (double)H / (double)n;                                  // stats.py:12
                 if (n > 1) {
-                    const unsigned __int128 num = (unsigned __int128)n * ssq - (unsigned __int128)H * H;
-                    sd = sqrt((double)num / ((double)n * (double)(n - 1)));    // stats.py:17-19
+                    // n * sum(x^2) - (sum x)^2 exactly in 128 bits (>= 0), then one conversion
+                    const unsigned long long a_lo = (unsigned long long)n * ssq, a_hi = __umul64hi(n, ssq);
+                    const unsigned long long b_lo = H * H, b_hi = __umul64hi(H, H);
+                    const unsigned long long d_lo = a_lo - b_lo, d_hi = a_hi - b_hi - (a_lo < b_lo ? 1ull : 0ull);
+                    const double num = (double)d_hi * 18446744073709551616.0 + (double)d_lo;
+                    sd = sqrt(num / ((double)n * (double)(n - 1)));            // stats.py:17-19
                 }
                 if (a.hist_bins && hist_ok) {
                     const unsigned long long fair = (H * (unsigned long long)n) / 2;   // Python-2 floor, stats.py:53
@@ -284,8 +288,8 @@ k_gini_sorted(const uint32_t *__restrict__ gaps, uint32_t n, double *__restrict_
         part += (unsigned long long)gaps[i] * (n - i);                        // rank i+1 ascending: n - rank + 1
         h += gaps[i];
     }
-    const unsigned long long sum_prefix = block_reduce(part, OpAddU64(), s_red64);
-    const unsigned long long H = block_reduce(h, OpAddU64(), s_red64);
+    const unsigned long long sum_prefix = block_reduce(part, OpAddU64(), 0ull, s_red64);
+    const unsigned long long H = block_reduce(h, OpAddU64(), 0ull, s_red64);
     if (threadIdx.x == 0) {
         double gini = __longlong_as_double(0x7ff8000000000000ll);
         const unsigned long long fair = (H * (unsigned long long)n) / 2;
@@ -363,7 +367,7 @@ extern "C" int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const
     a.gap_out = (uint32_t *)ctx->sort_keys[0].p;
     a.gap_count = (uint32_t *)(tmp + 16);
     const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS);
-    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_score<<<1, SC_THREADS, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     uint32_t ng = 0;

@@ -85,9 +85,10 @@ class SiteLists(object):
     def __init__(self, sites, site_off, n_primers, genome_len, list_of_primer=None, device=None):
         import torch
         self.lib = _lib.load()
-        self.ctx = _lib.context(device if device is not None else (sites.device.index if hasattr(sites, "device") else None))
+        is_t = isinstance(sites, torch.Tensor)
+        self.ctx = _lib.context(device if device is not None else (sites.device.index if is_t else None))
         self.dev = torch.device("cuda", self.ctx.device)
-        self.sites = sites if hasattr(sites, "device") else torch.from_numpy(
+        self.sites = sites if is_t else torch.from_numpy(
             np.ascontiguousarray(sites, dtype=np.uint32).view(np.int32)).to(self.dev)
         self.site_off = np.ascontiguousarray(site_off, dtype=np.uint64)
         self.n_lists = len(self.site_off) - 1
@@ -214,7 +215,7 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
         stream = torch.cuda.current_stream().cuda_stream
         if d_sets is None:
             d_sets = torch.from_numpy(np.ascontiguousarray(mapped)).to(dev)
-        d_bg = bg_dist_mean if hasattr(bg_dist_mean, "device") else torch.from_numpy(
+        d_bg = bg_dist_mean if isinstance(bg_dist_mean, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(bg_dist_mean, dtype=np.float64)).to(dev)
         o_n = torch.empty(S, dtype=torch.int32, device=dev)
         o_max = torch.empty(S, dtype=torch.int32, device=dev)
