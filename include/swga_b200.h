@@ -56,6 +56,9 @@ const char *swga_last_error(void);
 int  swga_ctx_create(int device, swga_ctx **out);
 void swga_ctx_destroy(swga_ctx *ctx);
 int  swga_ctx_sm_count(const swga_ctx *ctx);
+/* Counting kernel choice: 0 = automatic (partitioned shared-memory histograms when the shape allows,
+ * else direct L2 reds), 1 = always the direct red.global kernel, 2 = partitioned or fail. */
+int  swga_ctx_set_count_impl(swga_ctx *ctx, int impl);
 
 /* ---- memory helpers for hosts that do not bring their own allocator ------------------------- */
 int swga_malloc(swga_ctx *ctx, void **d_ptr, size_t bytes);

@@ -23,6 +23,7 @@ SIGNATURES = {
     "swga_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_ctx)]),
     "swga_ctx_destroy": (None, [c_ctx]),
     "swga_ctx_sm_count": (ctypes.c_int, [c_ctx]),
+    "swga_ctx_set_count_impl": (ctypes.c_int, [c_ctx, ctypes.c_int]),
     "swga_malloc": (ctypes.c_int, [c_ctx, ctypes.POINTER(c_vp), ctypes.c_size_t]),
     "swga_free": (ctypes.c_int, [c_ctx, c_vp]),
     "swga_host_alloc": (ctypes.c_int, [c_ctx, ctypes.POINTER(c_vp), ctypes.c_size_t]),

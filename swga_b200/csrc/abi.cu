@@ -69,7 +69,7 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_buf(c->packed); free_buf(c->brk); free_buf(c->fwd); free_buf(c->canon); free_buf(c->recs);
-    free_buf(c->scratch); free_buf(c->sort_hist); free_buf(c->score_tmp);
+    free_buf(c->scratch); free_buf(c->sort_hist); free_buf(c->score_tmp); free_buf(c->bucket_data); free_buf(c->bucket_meta);
     for (int i = 0; i < 2; ++i) { free_buf(c->sort_keys[i]); free_buf(c->sort_vals[i]); }
     for (int i = 0; i < 2; ++i) {
         free_buf(c->ascii[i]); free_buf(c->packed2[i]); free_buf(c->brk2[i]);
@@ -82,6 +82,12 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
 }
 
 extern "C" int swga_ctx_sm_count(const swga_ctx *c) { return c ? c->sm_count : 0; }
+extern "C" int swga_ctx_set_count_impl(swga_ctx *c, int impl)
+{
+    ARG_CHECK(c && impl >= 0 && impl <= 2);
+    c->count_impl = impl;
+    return SWGA_OK;
+}
 
 int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes)
 {

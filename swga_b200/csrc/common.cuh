@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 
 #include "../../include/swga_b200.h"
 
@@ -47,7 +48,8 @@ struct swga_ctx {
     cudaStream_t s_copy = nullptr, s_comp = nullptr;   // used by the *_host pipelines
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf packed, brk, ascii[2], packed2[2], brk2[2], fwd, canon, recs, scratch;
-    DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp;
+    DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp, bucket_data, bucket_meta;
+    int count_impl = 0;                                // 0 = auto, 1 = direct red.global kernel, 2 = partitioned
 };
 
 int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes);   // grow-only workspace

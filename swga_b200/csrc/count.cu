@@ -232,6 +232,9 @@ k_bench_atom_shared(uint32_t mask, uint64_t ops_per_thread, uint32_t *__restrict
     if (threadIdx.x == 0) atomicAdd(sink, sh[0]);
 }
 
+int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n_starts,
+                                      int kmin, int kmax, uint32_t *d_tables, cudaStream_t stream, int *done);
+
 // ------------------------------------------------------------------------------------------------
 // C ABI wrappers
 // ------------------------------------------------------------------------------------------------
@@ -305,6 +308,16 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     ARG_CHECK(ctx && d_packed && d_brk && d_tables);
     TRY(check_k(kmin, kmax));
     if (n_starts == 0) return SWGA_OK;
+    if (ctx->count_impl != 1) {
+        int done = 0;
+        TRY(swga_count_accumulate_partitioned(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, as_stream(stream),
+                                              &done));
+        if (done) return SWGA_OK;
+        if (ctx->count_impl == 2) {
+            swga_set_error("partitioned counting does not cover kmax=%d n_starts=%llu", kmax, (unsigned long long)n_starts);
+            return SWGA_E_ARG;
+        }
+    }
     const uint64_t threads = (n_starts + 31) / 32;
     k_count<<<grid_for(threads, 256), 256, 0, as_stream(stream)>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables,
                                                                   swga_make_offs(kmin, kmax));

@@ -152,3 +152,33 @@ def test_properties_at_scale(torch_cuda):
             up = fwd[o1:o1 + 4 ** (k + 1)].astype(np.int64).reshape(-1, 4).sum(1)
             diff = fwd[o0:o1].astype(np.int64) - up
             assert (diff >= 0).all() and int(diff.sum()) == n_rec      # one tail k-mer per record per level
+
+
+@pytest.mark.parametrize("kmin,kmax", [(5, 12), (8, 8), (6, 13), (9, 10)])
+def test_partitioned_kernel_equals_direct_and_oracle(kmin, kmax, oracle, torch_cuda):
+    """The partitioned shared-memory counting path (csrc/count_part.cu) against the direct red.global
+    kernel and the oracle, on a genome with N runs, IUPAC bytes and short records (mode A)."""
+    torch = torch_cuda
+    from swga_b200 import _lib, kmers, synth
+    lib, ctx = _lib.load(), _lib.context(0)
+    n = 6_000_011
+    seq = synth.bases(41, 0, n, 0.25)
+    runs = synth.splitmix64(np.arange(300, dtype=np.uint64) + np.uint64(13 << 40))
+    for r in runs:
+        p = int(r % np.uint64(n))
+        seq[p:p + int((r >> np.uint64(40)) % np.uint64(40)) + 1] = ord("N")
+    seq[123_456] = ord("R")
+    rs = np.array(sorted({0, 5, 999_999, 1_000_000, 3_000_017, 3_000_020, n}), dtype=np.uint64)
+    d = torch.from_numpy(seq).cuda()
+    out = {}
+    try:
+        for impl in (1, 2):
+            _lib.check(lib.swga_ctx_set_count_impl(ctx.h, impl))
+            _, canon = kmers.count_all_device(d, rs, mode_b=False, kmin=kmin, kmax=kmax)
+            torch.cuda.synchronize()
+            out[impl] = u32(canon)
+    finally:
+        _lib.check(lib.swga_ctx_set_count_impl(ctx.h, 0))
+    assert np.array_equal(out[1], out[2])
+    want = oracle.count_dense_allk(seq, rs, kmin, kmax, mode_b=0)
+    assert np.array_equal(out[2], want)
