@@ -308,19 +308,21 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     ARG_CHECK(ctx && d_packed && d_brk && d_tables);
     TRY(check_k(kmin, kmax));
     if (n_starts == 0) return SWGA_OK;
+    cudaStream_t st = as_stream(stream);
+    const TableOffs offs = swga_make_offs(kmin, kmax);
+    // Partitioned shared-memory path when the shape allows it (count_part.cu), else direct L2 reds.
+    // (Running the two concurrently on split ranges was measured in round 1 and does not overlap: both
+    // are limited by the per-SM LSU issue path -- profiles/r01_summary.md.)
     if (ctx->count_impl != 1) {
         int done = 0;
-        TRY(swga_count_accumulate_partitioned(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, as_stream(stream),
-                                              &done));
+        TRY(swga_count_accumulate_partitioned(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, st, &done));
         if (done) return SWGA_OK;
         if (ctx->count_impl == 2) {
             swga_set_error("partitioned counting does not cover kmax=%d n_starts=%llu", kmax, (unsigned long long)n_starts);
             return SWGA_E_ARG;
         }
     }
-    const uint64_t threads = (n_starts + 31) / 32;
-    k_count<<<grid_for(threads, 256), 256, 0, as_stream(stream)>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables,
-                                                                  swga_make_offs(kmin, kmax));
+    k_count<<<grid_for((n_starts + 31) / 32, 256), 256, 0, st>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables, offs);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }

@@ -14,9 +14,9 @@
 #include "common.cuh"
 
 #define PT_THREADS 512
-#define PT_ROUNDS 2
+#define PT_ROUNDS 1
 #define PT_GROUPS (PT_THREADS * PT_ROUNDS)          // groups of 32 starts per tile
-#define PT_TILE (PT_GROUPS * 32)                    // 32768 starts per tile
+#define PT_TILE (PT_GROUPS * 32)                    // 16384 starts per tile
 #define PT_LB 14                                    // low bits kept per element (uint16), 16384-bin tables
 #define PT_MAX_PB 12                                // at most 4096 buckets
 #define BC_THREADS 512
@@ -101,8 +101,8 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     const uint32_t nb = 1u << pb;
     uint32_t *cnt = sm;                      // [nb] per-tile bucket counts (then reused as running ranks)
     uint32_t *start = cnt + nb;              // [nb] exclusive scan of cnt
-    uint32_t *gbase = start + nb;            // [nb] reserved global offsets
-    uint16_t *staging = reinterpret_cast<uint16_t *>(gbase + nb);   // [PT_TILE]
+    uint32_t *goff = start + nb;             // [nb] (reserved global offset) - (start in tile)
+    uint32_t *staging = goff + nb;           // [PT_TILE] (bucket << 16) | low bits, bucket-sorted
     __shared__ uint32_t s_wsum[PT_THREADS / 32];
     const int lb = 2 * kmax - pb;
     const int sh_code = 32 - 2 * kmax;
@@ -162,7 +162,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 for (uint32_t i = 0; i < per; ++i) {
                     const uint32_t c = cnt[b0 + i];
                     start[b0 + i] = run;
-                    gbase[b0 + i] = c ? atomicAdd(cursor + b0 + i, c) : 0u;
+                    goff[b0 + i] = (c ? atomicAdd(cursor + b0 + i, c) : 0u) - run;
                     run += c;
                 }
         }
@@ -175,18 +175,18 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 for (int o = 0; o < 32; ++o) {
                     const uint32_t c = code_at(G[r], o, sh_code);
                     const uint32_t rank = (rk[r][o >> 1] >> ((o & 1) * 16)) & 0xffffu;
-                    staging[start[c >> lb] + rank] = (uint16_t)(c & lmask);
+                    staging[start[c >> lb] + rank] = ((c >> lb) << 16) | (c & lmask);
                 }
             }
         }
         __syncthreads();
-        // ---- write every bucket's run to its reserved global range ----
-        for (uint32_t b = warp; b < nb; b += PT_THREADS / 32) {
-            const uint32_t c = cnt[b];
-            if (c == 0) continue;
-            const uint32_t s = start[b];
-            uint16_t *dst = bucket_data + gbase[b];
-            for (uint32_t i = lane; i < c; i += 32) dst[i] = staging[s + i];
+        // ---- write out: slot j of the bucket-sorted tile goes to goff[bucket] + j (runs are contiguous) ----
+        {
+            const uint32_t total = start[nb - 1] + cnt[nb - 1];
+            for (uint32_t j = tid; j < total; j += PT_THREADS) {
+                const uint32_t e = staging[j];
+                bucket_data[goff[e >> 16] + j] = (uint16_t)e;
+            }
         }
         __syncthreads();
     }
@@ -266,6 +266,13 @@ k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restr
 int swga_exclusive_scan(swga_ctx *ctx, const uint32_t *d_in, uint64_t n, uint32_t *d_out, uint32_t *d_total,
                         cudaStream_t stream);
 
+int swga_count_partition_supported(uint64_t n_starts, int kmax, int *ok)
+{
+    const int pb = 2 * kmax - PT_LB;
+    *ok = !(pb < 1 || pb > PT_MAX_PB || n_starts < (1u << 22) || n_starts >= 0xfff00000ull);
+    return SWGA_OK;
+}
+
 // Partitioned accumulate.  Returns SWGA_OK and sets *done = 1 when it handled the request, *done = 0
 // when the shape is outside its range (the caller then uses the direct kernel).
 int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n_starts,
@@ -273,7 +280,9 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
 {
     *done = 0;
     const int pb = 2 * kmax - PT_LB;
-    if (pb < 1 || pb > PT_MAX_PB || n_starts < (1u << 22) || n_starts >= 0xfff00000ull) return SWGA_OK;
+    int ok = 0;
+    swga_count_partition_supported(n_starts, kmax, &ok);
+    if (!ok) return SWGA_OK;
     const uint32_t nb = 1u << pb;
     const TableOffs offs = swga_make_offs(kmin, kmax);
     // workspace: bucket data (2 B per start) + bucket_cnt[nb+2] + cursor[nb] + item_prefix[nb+1] + work counter
@@ -290,7 +299,7 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     TRY(swga_exclusive_scan(ctx, base, nb, base, base + nb, stream));
     CUDA_TRY(cudaMemcpyAsync(cursor, base, nb * 4, cudaMemcpyDeviceToDevice, stream));
     const uint32_t n_tiles = (uint32_t)((n_starts + PT_TILE - 1) / PT_TILE);
-    const size_t smem_p = (size_t)3 * nb * 4 + (size_t)PT_TILE * 2;
+    const size_t smem_p = (size_t)3 * nb * 4 + (size_t)PT_TILE * 4;
     CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     const int per_sm_p = smem_p <= 100 * 1024 ? 2 : 1;
     const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * per_sm_p);
