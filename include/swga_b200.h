@@ -149,6 +149,18 @@ int   swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n,
                              int kmin, int kmax, uint64_t n_starts, uint32_t *d_fwd);
 void *swga_ctx_compute_stream(swga_ctx *ctx);
 
+/* The count -> primer-row merge of `swga count` (swga/commands/count.py:98-135) over the canonical
+ * tables of the foreground, the background and (optionally, may be NULL) the exclusion sequences:
+ * a k-mer survives when fg >= max(1, min_fg_bind), bg <= max_bg_bind (negative = no limit), its
+ * exclusion count is below exclude_threshold, and max_sequential_nt(seq, seq) <= max_dimer_bp
+ * (swga/kmers.py:59-91).  Survivors are appended to d_rows as (k, code, fg_freq, bg_freq) uint32
+ * quadruples (16-byte aligned) in unspecified order; *d_n_rows receives the number of survivors, which
+ * may exceed row_capacity (only the first row_capacity are stored: call again with a larger buffer). */
+int swga_filter_primers(swga_ctx *ctx, const uint32_t *d_canon_fg, const uint32_t *d_canon_bg,
+                        const uint32_t *d_canon_ex, int kmin, int kmax, uint32_t min_fg_bind,
+                        int64_t max_bg_bind, int max_dimer_bp, uint32_t exclude_threshold,
+                        uint32_t *d_rows, uint32_t row_capacity, uint32_t *d_n_rows, void *stream);
+
 /* DSK result-file writer (ext/dsk/minia/SortingCount.cpp:149-156,649-653; read back by
  * swga/kmers.py:94-115): [i32 64][i32 k] then (u64 code, u32 count) for every count >= threshold. */
 int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,

@@ -42,5 +42,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_set_finder(ref="/root/reference"):
+    """Compile the reference's set_finder (cliquer + swga front end) UNCHANGED from its own sources,
+    where they lie, into swga_b200/bin/ -- the host remainder of the path.  Returns the path, or None
+    when neither a prebuilt binary nor the reference sources are available."""
+    out = os.path.join(HERE, "bin", "set_finder")
+    if os.access(out, os.X_OK):
+        return out
+    src = os.path.join(ref, "ext", "cliquer")
+    files = [os.path.join(src, f) for f in ("set_finder.c", "cliquer.c", "graph.c", "reorder.c")]
+    if not all(os.path.isfile(f) for f in files):
+        return None
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    # flags of ext/cliquer/Makefile:10,26
+    subprocess.check_call(["gcc", "-O3", "-fomit-frame-pointer", "-funroll-loops", "-w", "-DENABLE_LONG_OPTIONS"]
+                          + files + ["-o", out])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_set_finder())
