@@ -54,10 +54,10 @@ def test_count_primers_matches_reference_merge(workspace, oracle):
 def test_filter_and_find_sets_match_oracle(workspace, oracle):
     from swga_b200 import fasta, locate, pipeline, score
     d, fg, bg, ex = workspace
-    rows = pipeline.count_primers(fg, bg, None, min_size=6, max_size=8, min_fg_bind=20, max_bg_bind=60, max_dimer_bp=3)
+    rows = pipeline.count_primers(fg, bg, None, min_size=7, max_size=8, min_fg_bind=20, max_bg_bind=300, max_dimer_bp=3)
     primers = [pipeline.Primer(r["seq"], r["fg_freq"], r["bg_freq"], r["ratio"]) for r in rows]
     gi = locate.GenomeIndex(fg)
-    active = pipeline.filter_primers(primers, gi, min_fg_bind=20, max_bg_bind=60, max_primers=40, max_gini=0.8)
+    active = pipeline.filter_primers(primers, gi, min_fg_bind=20, max_bg_bind=300, max_primers=40, max_gini=0.8)
     assert 5 < len(active) <= 40
     recs = oracle.fasta_records_pyfaidx(open(fg, "rb").read())
     ends = oracle.chromosome_ends(recs)
@@ -68,14 +68,14 @@ def test_filter_and_find_sets_match_oracle(workspace, oracle):
         assert p.gini == oracle.gini(oracle.seq_diff(lin))
     bg_len = fasta.read_fasta(bg).n_bases
     graph = str(d / "compatibility_graph.dimacs")
-    found = pipeline.find_sets(active, gi, bg_len, min_bg_bind_dist=20000, max_fg_bind_dist=15000, min_size=2,
+    found = pipeline.find_sets(active, gi, bg_len, min_bg_bind_dist=3000, max_fg_bind_dist=15000, min_size=2,
                                max_size=4, max_dimer_bp=3, max_sets=25, graph_fp=graph)
     assert 0 < len(found) <= 25 and [r["_id"] for r in found] == list(range(1, len(found) + 1))
     # replay the same set_finder stream through the oracle's process_lines loop
     from swga_b200 import sets
     by_id = {p._id: p for p in active}
     passed = []
-    gen = sets.find(min_bg_bind_dist=20000, min_size=2, max_size=4, bg_length=bg_len, graph_fp=graph)
+    gen = sets.find(min_bg_bind_dist=3000, min_size=2, max_size=4, bg_length=bg_len, graph_fp=graph)
     for line in gen:
         ids, bgm = oracle.read_set_finder_line(line)
         sc, var, md = oracle.score_set([by_id[i].locations for i in ids], 15000, bgm, ends)
@@ -91,7 +91,7 @@ def test_filter_and_find_sets_match_oracle(workspace, oracle):
         assert row["fg_dist_std"] == pytest.approx(var["fg_dist_std"], rel=1e-9)
         assert row["score"] == pytest.approx(sc, rel=1e-12)
     # a custom expression is evaluated with the reference's namespace
-    found2 = pipeline.find_sets(active, gi, bg_len, 20000, 15000, 2, 4, max_sets=3, graph_fp=graph,
+    found2 = pipeline.find_sets(active, gi, bg_len, 3000, 15000, 2, 4, max_sets=3, graph_fp=graph,
                                 score_expression="fg_max_dist / set_size")
     for row in found2:
         assert row["score"] == row["fg_max_dist"] // row["set_size"]       # Python-2 integer division
