@@ -210,6 +210,9 @@ int swga_tile_offsets(swga_ctx *ctx, const uint32_t *d_sites, const uint64_t *d_
  * Outputs per set: n_sites (unique positions), max_dist, mean / stdev / gini of the gaps, the default
  * score (mean*gini)/bg_dist_mean, status bit0 = passed (interactive or max_dist <= max_fg_bind_dist),
  * bit1 = largest gap beyond the in-kernel histogram (gini is NaN: use swga_gini_unbounded). */
+/* Sets with at most `cap` raw sites (a power of two, 64..16384; 0 disables) are scored by the shared-memory
+ * sort kernel, the rest by the bitmap-tile kernel; results are identical.  Default 4096. */
+int swga_ctx_set_score_sort_cap(swga_ctx *ctx, uint32_t cap);
 uint32_t swga_score_tile_shift(void);
 uint32_t swga_score_max_hist_bins(void);
 int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,

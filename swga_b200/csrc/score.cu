@@ -45,6 +45,8 @@ struct ScoreArgs {
     // optional gap dump for the unbounded path (single set): gaps of set 0 are appended here
     uint32_t *gap_out;
     uint32_t *gap_count;
+    uint32_t sort_cap;           // sets with at most this many raw sites are scored by k_score_sort, the rest by k_score
+    uint32_t *work;              // [2] dynamic work counters (k_score_sort, k_score)
 };
 
 __device__ __forceinline__ uint32_t phys(uint32_t w) { return w + (w >> 5); }
@@ -99,7 +101,13 @@ k_score(ScoreArgs a)
     for (uint32_t i = tid; i < SC_L0_PHYS + SC_L1_WORDS + a.hist_bins; i += SC_THREADS) smem[i] = 0;
     __syncthreads();
 
-    for (uint32_t s = blockIdx.x; s < a.S; s += gridDim.x) {
+    __shared__ uint32_t s_set;
+    for (;;) {
+        if (tid == 0) s_set = a.work ? atomicAdd(a.work + 1, 1u) : 0xffffffffu;
+        __syncthreads();
+        uint32_t s = s_set;
+        if (!a.work) s = blockIdx.x;                      // single-set use (swga_gini_unbounded)
+        if (s >= a.S) break;
         // ---- members of this set (+ the record-bounds list) ----
         if (tid == 0) {
             uint32_t n = 0;
@@ -112,6 +120,14 @@ k_score(ScoreArgs a)
         }
         __syncthreads();
         const uint32_t nl = s_nlists;
+        if (a.sort_cap) {                                  // small sets belong to k_score_sort
+            uint32_t raw = 0;
+            for (uint32_t l = 0; l < nl; ++l) {
+                const uint32_t *row = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1);
+                raw += row[a.n_tiles] - row[0];
+            }
+            if (raw <= a.sort_cap) { __syncthreads(); continue; }
+        }
 
         uint32_t cnt = 0, maxgap = 0, first = 0xffffffffu;
         unsigned long long sumsq = 0;
@@ -275,6 +291,164 @@ k_score(ScoreArgs a)
             a.status[s] = (uint8_t)((passed ? 1 : 0) | ((!hist_ok) ? 2 : 0));
         }
         __syncthreads();
+        if (!a.work) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse sets: all raw sites of the set fit in shared memory -> gather, bitonic sort, adjacent
+// differences (duplicates dropped), and for sets that pass the max_dist filter a second sort of the
+// gaps gives Gini's rank-weighted sum directly.  128 threads per set, several CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+#define SS_THREADS 128
+#define SS_WARPS (SS_THREADS / 32)
+
+#define SS_CHUNK 256u                                   // elements one warp sorts without block-wide barriers
+
+__device__ __forceinline__ void bitonic_cx(uint32_t *buf, uint32_t i, uint32_t j, uint32_t k)
+{
+    const uint32_t lo = ((i & ~(j - 1u)) << 1) | (i & (j - 1u)), hi = lo + j;   // j is a power of two
+    const uint32_t x = buf[lo], y = buf[hi];
+    if ((x > y) == ((lo & k) == 0)) { buf[lo] = y; buf[hi] = x; }
+}
+
+// ascending bitonic sort of buf[0..n2), n2 a power of two >= 2.  Strides >= SS_CHUNK are block-wide
+// steps; once the stride drops below SS_CHUNK every exchange stays inside an aligned SS_CHUNK block, so
+// one warp finishes the whole block with warp-level barriers only.
+__device__ __forceinline__ void bitonic_sort_smem(uint32_t *buf, uint32_t n2)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t clen = n2 < SS_CHUNK ? n2 : SS_CHUNK, n_chunks = n2 / clen;
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j >= SS_CHUNK; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (n2 >> 1); i += SS_THREADS) bitonic_cx(buf, i, j, k);
+            __syncthreads();
+        }
+        for (uint32_t c = warp; c < n_chunks; c += SS_WARPS) {
+            const uint32_t half = clen >> 1, ibase = c * half;      // pair indices [ibase, ibase + half) live in chunk c
+            for (uint32_t jj = j; jj > 0; jj >>= 1) {
+                for (uint32_t i = lane; i < half; i += 32) bitonic_cx(buf, ibase + i, jj, k);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce_ss(T v, Op op, T ident, T *scratch /* SS_WARPS + 1 */)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T w = ident;
+#pragma unroll
+    for (int i = 0; i < SS_WARPS; ++i) w = op(w, scratch[i]);
+    return w;
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
+k_score_sort(ScoreArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t *buf = smem;                       // [cap2] positions
+    uint32_t *gaps = smem + a.sort_cap;         // [cap2] gaps (sort_cap is a power of two)
+    __shared__ uint32_t s_src[SC_MAX_LISTS], s_len[SC_MAX_LISTS], s_dst[SC_MAX_LISTS];
+    __shared__ uint32_t s_nl, s_raw, s_set;
+    __shared__ uint32_t r32[SS_WARPS + 1];
+    __shared__ unsigned long long r64[SS_WARPS + 1];
+    const uint32_t tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_set = atomicAdd(a.work, 1u);
+        __syncthreads();
+        const uint32_t s = s_set;
+        if (s >= a.S) break;
+        if (tid == 0) {
+            uint32_t n = 0, raw = 0;
+            for (uint32_t j = 0; j <= a.max_m && n < SC_MAX_LISTS; ++j) {
+                int32_t id = j < a.max_m ? a.sets[(uint64_t)s * a.max_m + j] : (int32_t)a.bounds_list;
+                if (id < 0) continue;
+                const uint32_t *row = a.toff + (uint64_t)id * (a.n_tiles + 1);
+                const uint32_t lo = row[0], len = row[a.n_tiles] - lo;
+                s_src[n] = lo; s_len[n] = len; s_dst[n] = raw;
+                raw += len; ++n;
+            }
+            s_nl = n; s_raw = raw;
+        }
+        __syncthreads();
+        const uint32_t raw = s_raw, nl = s_nl;
+        if (raw > a.sort_cap) { __syncthreads(); continue; }          // k_score takes it
+        uint32_t n2 = 2;
+        while (n2 < raw) n2 <<= 1;
+        for (uint32_t l = 0; l < nl; ++l) {
+            const uint32_t len = s_len[l];
+            const uint32_t *src = a.sites + s_src[l];
+            uint32_t *dst = buf + s_dst[l];
+            for (uint32_t i = tid; i < len; i += SS_THREADS) dst[i] = src[i];
+        }
+        for (uint32_t i = raw + tid; i < n2; i += SS_THREADS) buf[i] = 0xffffffffu;
+        __syncthreads();
+        bitonic_sort_smem(buf, n2);
+        // gaps between distinct neighbours; duplicates and padding become the sentinel
+        uint32_t cnt = 0, maxgap = 0;
+        unsigned long long sumsq = 0;
+        for (uint32_t i = tid; i < n2; i += SS_THREADS) {
+            uint32_t g = 0xffffffffu;
+            if (i + 1 < raw) {
+                const uint32_t d = buf[i + 1] - buf[i];
+                if (d) {
+                    g = d; ++cnt; maxgap = max(maxgap, d);
+                    sumsq += (unsigned long long)d * d;
+                }
+            }
+            gaps[i] = g;
+        }
+        const uint32_t n = block_reduce_ss(cnt, OpAddU32(), 0u, r32);
+        const uint32_t mx = block_reduce_ss(maxgap, OpMaxU32(), 0u, r32);
+        const unsigned long long ssq = block_reduce_ss(sumsq, OpAddU64(), 0ull, r64);
+        const unsigned long long H = raw ? (unsigned long long)(buf[raw - 1] - buf[0]) : 0ull;
+        const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
+        unsigned long long sum_prefix = 0;
+        if (passed && n > 0) {
+            __syncthreads();
+            bitonic_sort_smem(gaps, n2);
+            unsigned long long part = 0;
+            for (uint32_t i = tid; i < n; i += SS_THREADS) part += (unsigned long long)gaps[i] * (n - i);
+            sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
+        }
+        if (tid == 0) {
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            double mean = nan, sd = nan, gini = nan, score = nan;
+            if (n > 0) {
+                mean = (double)H / (double)n;
+                if (n > 1) {
+                    const unsigned long long a_lo = (unsigned long long)n * ssq, a_hi = __umul64hi(n, ssq);
+                    const unsigned long long b_lo = H * H, b_hi = __umul64hi(H, H);
+                    const unsigned long long d_lo = a_lo - b_lo, d_hi = a_hi - b_hi - (a_lo < b_lo ? 1ull : 0ull);
+                    const double num = (double)d_hi * 18446744073709551616.0 + (double)d_lo;
+                    sd = sqrt(num / ((double)n * (double)(n - 1)));
+                }
+                if (passed) {
+                    const unsigned long long fair = (H * (unsigned long long)n) / 2;
+                    if (fair > 0) {
+                        const long long two_area = (long long)(2 * sum_prefix) - (long long)H;
+                        gini = (double)((long long)(2 * fair) - two_area) / (double)(2 * fair);
+                    }
+                }
+                score = (mean * gini) / a.bg_dist_mean[s];
+            }
+            a.n_sites[s] = raw ? n + 1 : 0;
+            a.max_dist[s] = mx;
+            a.mean[s] = mean;
+            a.stdev[s] = sd;
+            a.gini[s] = gini;
+            a.score[s] = score;
+            a.status[s] = (uint8_t)(passed ? 1 : 0);
+        }
+        __syncthreads();
     }
 }
 
@@ -332,11 +506,31 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
     a.hist_bins = (uint32_t)(want < cap ? want : cap);
     a.n_sites = d_n_sites; a.max_dist = d_max_dist; a.mean = d_mean; a.stdev = d_stdev; a.gini = d_gini;
     a.score = d_score; a.status = d_status;
+    // sparse sets first (k_score_sort: gather + sort in shared memory), then the rest (k_score: bitmap tiles)
+    a.sort_cap = ctx->score_sort_cap;
+    TRY(swga_ensure(ctx, ctx->score_tmp, 256));
+    a.work = (uint32_t *)((uint8_t *)ctx->score_tmp.p + 128);
+    CUDA_TRY(cudaMemsetAsync(a.work, 0, 8, as_stream(stream)));
+    if (a.sort_cap) {
+        const size_t smem_s = 8ull * a.sort_cap;
+        CUDA_TRY(cudaFuncSetAttribute(k_score_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem_s + 1024)));
+        const uint32_t grid_s = std::min<uint32_t>(S, (uint32_t)ctx->sm_count * per_sm);
+        k_score_sort<<<grid_s, SS_THREADS, smem_s, as_stream(stream)>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
     const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS + a.hist_bins);
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = S < (uint32_t)ctx->sm_count ? S : (uint32_t)ctx->sm_count;
     k_score<<<grid, SC_THREADS, smem, as_stream(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}
+
+extern "C" int swga_ctx_set_score_sort_cap(swga_ctx *ctx, uint32_t cap)
+{
+    ARG_CHECK(ctx && (cap == 0 || ((cap & (cap - 1)) == 0 && cap >= 64 && cap <= 16384)));
+    ctx->score_sort_cap = cap;
     return SWGA_OK;
 }
 

@@ -160,17 +160,25 @@ def test_batched_scoring_matches_oracle(quirky, oracle):
     sets[0, 0] = len(primers) - 1                                            # a set of one rare primer
     bgs = rng.uniform(100, 1e5, S)
     bgs[1] = float("inf")
-    for max_fg, interactive in ((36000, False), (3000, False), (0, True)):
-        res = score.score_sets(sl, sets, bgs, max_fg, interactive=interactive)
-        want = _oracle_scores(oracle, locs_of, chr_ends, sets, bgs, max_fg, interactive)
-        n_pass = 0
-        for i in range(S):
-            _check(res, i, want[i], bgs[i])
-            n_pass += bool(res.passed[i])
-        assert n_pass > 0
-    # interactive sets include gaps far beyond the in-kernel histogram: the sort path was exercised
-    res = score.score_sets(sl, sets, bgs, 0, interactive=True)
-    assert ((res.status & 2) != 0).any()
+    from swga_b200 import _lib
+    lib, ctx = _lib.load(), _lib.context(0)
+    try:
+        for cap in (4096, 0, 256):                                           # sort kernel / bitmap kernel / mixed
+            _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, cap))
+            for max_fg, interactive in ((36000, False), (3000, False), (0, True)):
+                res = score.score_sets(sl, sets, bgs, max_fg, interactive=interactive)
+                want = _oracle_scores(oracle, locs_of, chr_ends, sets, bgs, max_fg, interactive)
+                n_pass = 0
+                for i in range(S):
+                    _check(res, i, want[i], bgs[i])
+                    n_pass += bool(res.passed[i])
+                assert n_pass > 0
+            if cap == 0:
+                # interactive sets include gaps far beyond the in-kernel histogram: the gap-sort path ran
+                res = score.score_sets(sl, sets, bgs, 0, interactive=True)
+                assert ((res.status & 2) != 0).any()
+    finally:
+        _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
 
 
 def test_reference_score_kats(oracle):
