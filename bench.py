@@ -128,31 +128,60 @@ def workload_name(w):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU through NVML every ~2 ms while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = None
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, timeout=5).stdout.decode()
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
             except Exception:
                 pass
-            time.sleep(0.05)
+            h = None
+            if uuid:
+                for pre in ("GPU-", ""):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID((pre + uuid).encode())
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((clk, mx, int(r)))
+                time.sleep(0.002)
+        except Exception as e:                      # NVML missing: fall back to nvidia-smi (slow, few samples)
+            self.error = repr(e)
+            q = "clocks.sm,clocks.max.sm"
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, timeout=5).stdout.decode()
+                    f = [float(x) for x in out.strip().split(",")]
+                    self.samples.append((f[0], f[1], 0))
+                except Exception:
+                    pass
+                time.sleep(0.05)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        sm = [s[0] for s in self.samples]
+        reasons = sorted({name for s in self.samples for name, bit in bits.items() if s[2] & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
@@ -355,6 +384,13 @@ def run_b200_arm(args):
         same = bool(torch.equal(h_canon_bg.to(dev), bg.canon))
         e2e["tables_equal_device_path"] = same
 
+    scoring = None
+    if rank == 0 and not args.no_extras:
+        try:
+            scoring = scoring_extra(dev)
+        except Exception as e:                      # the counting line must survive a failure of the extra
+            scoring = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         dt, bases, kind, cores = cpu_reference_pass(args.workload, args.cpu_sample_bases, 1)
@@ -372,10 +408,58 @@ def run_b200_arm(args):
                        if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
             "roofline": roofline, "path_roofline": path, "atomic": atomic, "cpu_baseline": cpu, "e2e": e2e,
             "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps,
+            "scoring": scoring,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
+
+
+def scoring_extra(dev):
+    """Second headline of BASELINE.json: candidate sets scored per second on one B200 (kernel (d)), device
+    resident site lists and sets, CUDA events.  Workload C4 of SURVEY.md 8(d) on a 2x10^5-set sample of the
+    10^7 (the 200 most frequent 8..12-mers of the 23 Mbp AT-rich foreground: ~2x10^5 unique sites per
+    set), plus a 'typical' variant with 200 12-mers of ~400 sites each (the scale of swga's default
+    min_fg_bind = 1e-5 * fg_length), 10^6 sets."""
+    import numpy as np
+    import torch
+    from swga_b200 import fasta, kmers, locate, score, synth, workloads
+    seed, n, gc, n_rec = synth.CONFIGS["C3_fg"]
+    g = fasta.Genome(synth.bases(seed, 0, n, gc), synth.equal_records(n, n_rec), ["chr%d" % (i + 1) for i in range(n_rec)])
+    tabs = kmers.count_all(g, 5, 12)
+    gi = locate.GenomeIndex(g)
+    out = {"unit": "sets/s", "fg_bases": n, "timing": "CUDA events, best of 3, device-resident inputs"}
+    t12 = tabs.table(12)
+    order = np.argsort(-t12.astype(np.int64), kind="stable")
+    lo = int(np.searchsorted(-t12[order].astype(np.int64), -400))
+    variants = {
+        "C4_dense": ([kmers.codes_to_kmers([c], k)[0] for k, c, _ in workloads.top_primers(tabs, 5, 12, 200)], 200_000),
+        "typical_400_sites": (kmers.codes_to_kmers(order[lo:lo + 200], 12), 1_000_000),
+    }
+    for name, (seqs, S) in variants.items():
+        sl = score.SiteLists.from_index(gi, seqs)
+        sets_, _ = workloads.c4_sets(S)
+        mapped = np.where(sets_ >= 0, sl.list_of_primer[np.clip(sets_, 0, 199)], -1).astype(np.int32)
+        d_sets = torch.from_numpy(mapped).to(dev)
+        bg = torch.full((S,), 1000.0, dtype=torch.float64, device=dev)
+        row = {"sets": S}
+        for label, max_fg in (("max_fg_36000", 36000), ("no_reject", 2 ** 31 - 1)):
+            best = None
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res = score.score_sets(sl, None, bg, max_fg, d_sets=d_sets, return_device=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            L = res.n_sites.cpu().numpy().view(np.uint32)
+            st = res.status.cpu().numpy()
+            row[label] = {"sets_per_s": S / best * 1e3, "ms": best, "mean_unique_sites_per_set": float(L.mean()),
+                          "passed_frac": float((st & 1).mean()),
+                          "merged_sites_per_s": float(sl.counts()[:-1].mean()) * 8 * S / best * 1e3}
+        out[name] = row
+    return out
 
 
 def main():
