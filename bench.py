@@ -251,9 +251,9 @@ def run_b200_arm(args):
                 td.all_reduce(self.fwd, op=td.ReduceOp.SUM)
             _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
             _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
-            # accumulate = k_bucket_hist + 3 scan kernels + k_partition + k_item_prefix + k_bucket_count when the
-            # partitioned path applies (>= 2^22 starts), else the single k_count
-            acc = 7 if (self.n_starts >= (1 << 22) and 1 <= 2 * KMAX - 14 <= 12) else 1
+            # accumulate = k_bucket_hist (sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count
+            # when the partitioned path applies (>= 2^22 starts, kmax 11 or 12), else the single k_count
+            acc = 5 if (self.n_starts >= (1 << 22) and 8 <= 2 * KMAX - 14 <= 10) else 1
             self.launches = k + acc + (KMAX - KMIN) + 1
 
     fg = Dev(fg_seed, n_fg, fg_gc, fg_nrec, shard=False)

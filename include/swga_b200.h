@@ -121,6 +121,11 @@ int swga_mark_records(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64_t n_re
 int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk,
                           uint64_t n_starts, int kmin, int kmax, uint32_t *d_tables, void *stream);
 int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *d_tables, void *stream);
+/* Diagnostics of the last partitioned swga_count_accumulate on this context (synchronises the device):
+ * h_stats[0] = elements that found their shared-memory staging range full, [1] = elements that found
+ * their global bucket full (added to the table directly), [2] = single-base-run groups of 32 starts,
+ * [3] = groups that took the direct path because they touch a break.  All zero when the direct kernel ran. */
+int swga_count_partition_stats(swga_ctx *ctx, uint64_t *h_stats);
 int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd,
                         uint32_t *d_canon, void *stream);
 

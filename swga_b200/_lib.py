@@ -42,6 +42,7 @@ SIGNATURES = {
     "swga_mark_records": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp]),
     "swga_count_accumulate": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                              c_vp, c_vp]),
+    "swga_count_partition_stats": (ctypes.c_int, [c_ctx, c_u64p]),
     "swga_count_finalize": (ctypes.c_int, [c_ctx, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
     "swga_fold_canonical": (ctypes.c_int, [c_ctx, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "swga_count_genome_device": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,

@@ -1,24 +1,41 @@
 // count_part.cu -- kernel (b), partitioned form: the same additive "top-k + tails" counts as k_count
 // (count.cu), but the updates of the top table T_kmax are taken out of the L2 atomic unit.
 //
-// Round-1 profile (profiles/r01_summary.md): k_count sits at the red.global ceiling (~190-210 G/s, LTS
-// 87 %, 8.3 B/base of DRAM traffic from evicted table sectors) while shared-memory atomics measure
-// ~2600 G/s.  So: (1) k_bucket_hist counts the kmax-mers per PREFIX (top `pb` bits of the code),
-// (2) k_partition scatters the low `lb = 2 kmax - pb` bits of every kmax-mer (uint16) into its
-// prefix bucket through a shared-memory counting sort of a 32 Ki-start tile (coalesced bucket runs),
-// (3) k_bucket_count histograms each bucket in a 2^lb-word shared-memory table and adds the non-zero
-// bins to T_kmax.  Groups of 32 starts that touch a break (record end, 'N', buffer end) keep the
-// direct path of k_count, so results are identical by construction.
+// Round-1 profile (profiles/r01_summary.md): k_count sits at the red.global ceiling (~190 G/s, LTS 87 %)
+// while shared-memory atomics measure ~2600 G/s.  So the kmax-mers are first PARTITIONED by the top
+// `pb` bits of their code into nb = 2^pb buckets (the low 14 bits stored as uint16), and each bucket is
+// then histogrammed in a 2^14-word shared-memory table:
+//
+//   (1) k_bucket_hist   counts the prefixes of a strided SAMPLE of the genome (1 warp-tile in `stride`);
+//   (2) k_bucket_layout turns the sample into (a) a global bucket layout -- estimated size + slack per
+//       bucket -- and (b) per-tile slot ranges inside the shared-memory staging area of k_partition;
+//   (3) k_partition     one tile = 16 Ki starts: every element takes its staging slot with ONE shared
+//       atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the tile's
+//       bucket runs are then copied to the buckets in coalesced pieces (one global atomicAdd per
+//       bucket and tile reserves the range);
+//   (4) k_bucket_count  shared-memory histogram of each bucket, added to T_kmax.
+//
+// Nothing depends on the sample being right: an element that finds its staging range full goes through
+// a small overflow list, an element that finds its global bucket full is added to T_kmax directly
+// (red.global), groups of 32 starts that touch a break (record end, 'N', buffer end) keep the direct
+// path of k_count, and single-base runs (poly-A, DSK mode B's N -> G) are one add of 32.  Results
+// are therefore identical to k_count by construction (tests/test_count_gpu.py).
 //
 // Reference results reproduced: as count.cu (Bank.cpp:889-902,1042-1070; OAHash.cpp:142-154).
 #include "common.cuh"
 
 #define PT_THREADS 512
-#define PT_ROUNDS 1
-#define PT_GROUPS (PT_THREADS * PT_ROUNDS)          // groups of 32 starts per tile
-#define PT_TILE (PT_GROUPS * 32)                    // 16384 starts per tile
+#define PT_TILE (PT_THREADS * 32)                   // 16384 starts per tile, one group of 32 per thread
 #define PT_LB 14                                    // low bits kept per element (uint16), 16384-bin tables
-#define PT_MAX_PB 12                                // at most 4096 buckets
+#define PT_MIN_PB 8                                 // kmax = 11
+#define PT_MAX_PB 10                                // kmax = 12
+#define PT_STAGE 52224u                             // uint16 staging slots per tile (102 KB)
+#ifndef PT_CH
+#define PT_CH 4                                     // elements per chunk: bucket runs are stored in whole chunks,
+#endif                                              // padded with PT_PAD (ignored by k_bucket_count)
+#define PT_PAD 0xFFFFu
+#define PT_OVF_CAP 512u                             // staging-overflow list entries per tile
+#define PT_ADD ((1u << 17) + 2u)                    // one element: guard += 1, byte address += 2
 #define BC_THREADS 512
 #define BC_ITEM (1u << 20)                          // elements per work item of k_bucket_count
 
@@ -45,9 +62,16 @@ __device__ __forceinline__ Group load_group(const uint32_t *__restrict__ packed,
     return r;
 }
 
-__device__ __forceinline__ uint32_t code_at(const Group &g, int o, int sh)
+// the 16 bases starting at offset o (0..31) of the group, first base in bits 31:30
+__device__ __forceinline__ uint32_t window(const Group &g, int o)
 {
-    return (o < 16 ? __funnelshift_l(g.w1, g.w0, 2 * o) : __funnelshift_l(g.w2, g.w1, 2 * (o - 16))) >> sh;
+    return o < 16 ? __funnelshift_l(g.w1, g.w0, 2 * o) : __funnelshift_l(g.w2, g.w1, 2 * (o - 16));
+}
+
+// all 32 kmax-mers of the group are the same single-base run
+__device__ __forceinline__ bool uniform_group(const Group &g, int kmax)
+{
+    return g.w0 == g.w1 && g.w0 == __funnelshift_l(g.w0, g.w0, 2) && ((g.w2 ^ g.w0) >> (34 - 2 * kmax)) == 0u;
 }
 
 // direct path for a group that touches a break or the end of the owned range (same as k_count's slow path)
@@ -68,22 +92,28 @@ __device__ __forceinline__ void slow_group(const uint32_t *__restrict__ packed, 
     }
 }
 
-// ---- (1) per-prefix counts of the fast groups ------------------------------------------------------
+// ---- (1) per-prefix counts of the fast groups of a strided sample ------------------------------------
+// Sampled group i is group (i / 32) * 32 * stride + (i % 32): one warp-tile of 1024 consecutive starts
+// out of every `stride`.
 __global__ void __launch_bounds__(PT_THREADS)
 k_bucket_hist(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmax,
-              int pb, uint32_t *__restrict__ bucket_cnt)
+              int pb, uint64_t n_sampled, uint32_t stride, uint32_t *__restrict__ bucket_cnt)
 {
     extern __shared__ uint32_t h[];
     const uint32_t nb = 1u << pb;
     for (uint32_t i = threadIdx.x; i < nb; i += PT_THREADS) h[i] = 0;
     __syncthreads();
-    const uint64_t n_groups = (n_starts + 31) / 32;
     const int sh = 32 - pb;
-    for (uint64_t g = blockIdx.x * (uint64_t)PT_THREADS + threadIdx.x; g < n_groups; g += (uint64_t)gridDim.x * PT_THREADS) {
+    for (uint64_t i = blockIdx.x * (uint64_t)PT_THREADS + threadIdx.x; i < n_sampled; i += (uint64_t)gridDim.x * PT_THREADS) {
+        const uint64_t g = (i >> 5) * 32 * stride + (i & 31);
         const Group G = load_group(packed, brk, g, n_starts, kmax);
         if (G.fast) {
+            if (uniform_group(G, kmax)) {
+                atomicAdd(&h[G.w0 >> sh], 32u);
+            } else {
 #pragma unroll
-            for (int o = 0; o < 32; ++o) atomicAdd(&h[code_at(G, o, sh)], 1u);
+                for (int o = 0; o < 32; ++o) atomicAdd(&h[window(G, o) >> sh], 1u);
+            }
         }
     }
     __syncthreads();
@@ -91,114 +121,264 @@ k_bucket_hist(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ 
         if (h[i]) atomicAdd(bucket_cnt + i, h[i]);
 }
 
-// ---- (2) scatter the low bits into prefix buckets --------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS)
-k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
-            int kmax, int pb, uint32_t *__restrict__ tables, TableOffs offs, uint32_t *__restrict__ cursor,
-            uint16_t *__restrict__ bucket_data, uint32_t n_tiles)
+// ---- (2) bucket layout from the sample -----------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_excl_scan_1024(unsigned long long v, unsigned long long *s_warp,
+                                                                    unsigned long long *total)
 {
-    extern __shared__ uint32_t sm[];
-    const uint32_t nb = 1u << pb;
-    uint32_t *cnt = sm;                      // [nb] per-tile bucket counts (then reused as running ranks)
-    uint32_t *start = cnt + nb;              // [nb] exclusive scan of cnt
-    uint32_t *goff = start + nb;             // [nb] (reserved global offset) - (start in tile)
-    uint32_t *staging = goff + nb;           // [PT_TILE] (bucket << 16) | low bits, bucket-sorted
-    __shared__ uint32_t s_wsum[PT_THREADS / 32];
-    const int lb = 2 * kmax - pb;
-    const int sh_code = 32 - 2 * kmax;
-    const uint32_t lmask = (1u << lb) - 1u;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = tid; i < nb; i += PT_THREADS) cnt[i] = 0;
-        __syncthreads();
-        Group G[PT_ROUNDS];
-        uint32_t rk[PT_ROUNDS][16];
-        // ---- pass A: rank of every element inside its bucket (for this tile) ----
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
 #pragma unroll
-        for (int r = 0; r < PT_ROUNDS; ++r) {
-            const uint64_t g = (uint64_t)tile * PT_GROUPS + (uint64_t)r * PT_THREADS + tid;
-            G[r] = load_group(packed, brk, g, n_starts, kmax);
-            if (G[r].fast) {
-#pragma unroll
-                for (int o = 0; o < 32; o += 2) {
-                    const uint32_t c0 = code_at(G[r], o, sh_code), c1 = code_at(G[r], o + 1, sh_code);
-                    const uint32_t r0 = atomicAdd(&cnt[c0 >> lb], 1u);
-                    const uint32_t r1 = atomicAdd(&cnt[c1 >> lb], 1u);
-                    rk[r][o >> 1] = r0 | (r1 << 16);
-                }
-            } else {
-                slow_group(packed, brk, g, n_starts, kmin, kmax, tables, offs);
-            }
-        }
-        __syncthreads();
-        // ---- exclusive scan of cnt -> start; reserve global space per bucket ----
-        {
-            const uint32_t per = nb / PT_THREADS ? nb / PT_THREADS : 1;      // nb is a power of two
-            uint32_t local = 0;
-            const uint32_t b0 = tid * per;
-            if (b0 < nb)
-                for (uint32_t i = 0; i < per; ++i) local += cnt[b0 + i];
-            uint32_t inc = local;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= (uint32_t)d) inc += o;
-            }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t v = lane < PT_THREADS / 32 ? s_wsum[lane] : 0, vi = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, vi, d);
-                    if (lane >= (uint32_t)d) vi += o;
-                }
-                if (lane < PT_THREADS / 32) s_wsum[lane] = vi - v;
-            }
-            __syncthreads();
-            uint32_t run = s_wsum[warp] + inc - local;
-            if (b0 < nb)
-                for (uint32_t i = 0; i < per; ++i) {
-                    const uint32_t c = cnt[b0 + i];
-                    start[b0 + i] = run;
-                    goff[b0 + i] = (c ? atomicAdd(cursor + b0 + i, c) : 0u) - run;
-                    run += c;
-                }
-        }
-        __syncthreads();
-        // ---- pass B: place the low bits at start[bucket] + rank ----
-#pragma unroll
-        for (int r = 0; r < PT_ROUNDS; ++r) {
-            if (G[r].fast) {
-#pragma unroll
-                for (int o = 0; o < 32; ++o) {
-                    const uint32_t c = code_at(G[r], o, sh_code);
-                    const uint32_t rank = (rk[r][o >> 1] >> ((o & 1) * 16)) & 0xffffu;
-                    staging[start[c >> lb] + rank] = ((c >> lb) << 16) | (c & lmask);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- write out: slot j of the bucket-sorted tile goes to goff[bucket] + j (runs are contiguous) ----
-        {
-            const uint32_t total = start[nb - 1] + cnt[nb - 1];
-            for (uint32_t j = tid; j < total; j += PT_THREADS) {
-                const uint32_t e = staging[j];
-                bucket_data[goff[e >> 16] + j] = (uint16_t)e;
-            }
-        }
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
     }
+    __syncthreads();                                           // s_warp may still be read by a previous scan
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = s_warp[lane];
+        unsigned long long wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += o;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + inc - v;
 }
 
-// ---- work items of phase 3: ceil(size_b / BC_ITEM) per bucket ----------------------------------------
-__global__ void k_item_prefix(const uint32_t *__restrict__ bucket_base, uint32_t nb, uint32_t *__restrict__ item_prefix)
+// Global slack of one bucket: 1/16 of the estimate + 8 sigma of the sampling noise + a constant.
+__host__ __device__ static inline unsigned long long bucket_slack(unsigned long long est, float sqrt_s, uint32_t ratio)
 {
-    // single block; nb <= 4096
-    __shared__ uint32_t s[4097];
+    return est / 16 + (unsigned long long)(8.0f * (float)ratio * sqrt_s) + 1024ull;
+}
+
+// single block of 1024 threads; nb <= 1024.  `pad` = expected padding per bucket (runs are stored in
+// chunks of PT_CH elements).
+__global__ void __launch_bounds__(1024)
+k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n_groups, uint64_t n_sampled,
+                uint32_t ratio, uint64_t pad, uint64_t capacity, uint32_t *__restrict__ base,
+                uint32_t *__restrict__ cursor, uint32_t *__restrict__ init)
+{
+    __shared__ unsigned long long s_warp[33];
+    const uint32_t b = threadIdx.x;
+    const uint32_t s = b < nb ? sample_cnt[b] : 0u;
+    unsigned long long S;
+    block_excl_scan_1024(s, s_warp, &S);
+    // (a) global layout
+    unsigned long long est = n_sampled ? (unsigned long long)s * n_groups / n_sampled : 0ull;
+    unsigned long long cap_g = 0;
+    if (b < nb) cap_g = (est + bucket_slack(est, sqrtf((float)s + 1.0f), ratio) + pad + 7ull) & ~7ull;
+    unsigned long long total;
+    unsigned long long off = block_excl_scan_1024(cap_g, s_warp, &total);
+    if (total > capacity) {                                    // cannot happen with the host's bound; stay in range anyway
+        off = (off * capacity / total) & ~7ull;
+        total = capacity & ~7ull;
+    }
+    if (b < nb) {
+        base[b] = (uint32_t)off;
+        cursor[b] = (uint32_t)off;
+    }
+    if (b == 0) base[nb] = (uint32_t)total;
+    // (b) staging slots per tile: 5/4 of the expected share of the tile + beta, a multiple of 8
+    const uint32_t beta = (PT_STAGE - PT_TILE * 5 / 4) / nb - 8;
+    unsigned long long cap_t = 0;
+    if (b < nb) {
+        const unsigned long long share = S ? (unsigned long long)s * (PT_TILE * 5 / 4) / S : 0ull;
+        cap_t = (min((unsigned long long)PT_TILE, share + beta) + 7ull) & ~7ull;
+    }
+    unsigned long long tot_t;
+    const unsigned long long start = block_excl_scan_1024(cap_t, s_warp, &tot_t);
+    if (b < nb) init[b] = ((0x4000u - (uint32_t)cap_t) << 17) | (uint32_t)(start * 2);
+}
+
+// ---- (3) scatter the low bits into prefix buckets --------------------------------------------------
+// A chunk of PT_CH staged elements (uint16 each) as one vector.
+template <int CH> struct Chunk;
+template <> struct Chunk<4> {
+    typedef uint2 vec;
+    static __device__ __forceinline__ void words(const vec &v, uint32_t *w) { w[0] = v.x; w[1] = v.y; }
+    static __device__ __forceinline__ vec make(const uint32_t *w) { return make_uint2(w[0], w[1]); }
+};
+template <> struct Chunk<8> {
+    typedef uint4 vec;
+    static __device__ __forceinline__ void words(const vec &v, uint32_t *w) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    static __device__ __forceinline__ vec make(const uint32_t *w) { return make_uint4(w[0], w[1], w[2], w[3]); }
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(PT_THREADS, 2)
+k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
+            uint32_t *__restrict__ tables, TableOffs offs, const uint32_t *__restrict__ base,
+            const uint32_t *__restrict__ init_g, uint32_t *__restrict__ cursor, uint16_t *__restrict__ data,
+            uint32_t n_tiles, unsigned long long *__restrict__ stats)
+{
+    constexpr int PB = 2 * KMAX - PT_LB, SH = 32 - 2 * KMAX;
+    constexpr uint32_t NB = 1u << PB, LMASK = (1u << PT_LB) - 1u;
+    constexpr int CH = PT_CH, LPB = 32 / CH, BPS = 32 / LPB;   // lanes per bucket, buckets per sub-round
+    constexpr int WARPS = PT_THREADS / 32, UNITS = NB / 32;      // a unit = 32 buckets, one per lane
+    constexpr int ROUNDS = (UNITS + WARPS - 1) / WARPS;        // units per warp
+    typedef typename Chunk<CH>::vec vec_t;
+    extern __shared__ __align__(16) uint32_t sm[];
+    uint32_t *fill = sm;                                       // [NB] (guard << 17) | byte address of the next slot
+    uint32_t *init = fill + NB;                                // [NB] value of fill at the start of a tile
+    uint32_t *ovf = init + NB;                                 // [PT_OVF_CAP] codes that found their staging range full
+    unsigned char *stg = reinterpret_cast<unsigned char *>(ovf + PT_OVF_CAP);   // [PT_STAGE] uint16
+    __shared__ uint32_t s_novf[2];                             // entries of `ovf`, by tile parity
+    __shared__ uint32_t s_stats[4];                            // exits taken: staging full, bucket full, uniform, slow groups
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *__restrict__ top = tables + offs.off[KMAX];
+    if (tid < 4) s_stats[tid] = 0;
+
+    for (uint32_t i = tid; i < NB; i += PT_THREADS) {
+        const uint32_t v = init_g[i];
+        init[i] = v;
+        fill[i] = v;
+    }
+    if (tid < 2) s_novf[tid] = 0;
+    __syncthreads();
+
+    uint32_t par = 0;
+    Group G = load_group(packed, brk, (uint64_t)blockIdx.x * PT_THREADS + tid, n_starts, KMAX);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t g = (uint64_t)tile * PT_THREADS + tid;
+        Group N;                                               // next tile's group: in flight during this tile
+        N.fast = false;
+        N.w0 = N.w1 = N.w2 = 0;
+        if (tile + gridDim.x < n_tiles) N = load_group(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, n_starts, KMAX);
+        // ---- every element takes its staging slot ----
+        if (G.fast) {
+            if (uniform_group(G, KMAX)) {
+                atomicAdd(top + (G.w0 >> SH), 32u);
+                atomicAdd(&s_stats[2], 1u);
+            } else {
+                uint32_t full = 0;                             // bit 31-o: element o found its range full
+#pragma unroll
+                for (int o = 0; o < 32; ++o) {
+                    const uint32_t W = window(G, o);
+                    const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
+                    const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
+                    if ((int32_t)old >= 0)
+                        *reinterpret_cast<uint16_t *>(stg + (old & 0x1FFFFu)) = (uint16_t)((W >> SH) & LMASK);
+                    full = __funnelshift_l(old, full, 1);
+                }
+                while (full) {                                 // rare: the tile's composition is off the sample's
+                    const int o = __clz(full);
+                    full &= ~(0x80000000u >> o);
+                    const uint32_t slot = atomicAdd(&s_novf[par], 1u);
+                    if (slot < PT_OVF_CAP) ovf[slot] = window(G, o) >> SH;
+                    else atomicAdd(top + (window(G, o) >> SH), 1u);   // list full too: straight to the table
+                }
+            }
+        } else {
+            slow_group(packed, brk, g, n_starts, kmin, KMAX, tables, offs);
+            if (g * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
+        }
+        __syncthreads();
+        // ---- per warp: reserve the global range of the runs of its buckets, re-arm their counters ----
+        uint32_t u_[ROUNDS], slot_[ROUNDS], at_[ROUNDS], nfit_[ROUNDS];
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t unit = r * WARPS + warp;
+            u_[r] = slot_[r] = at_[r] = nfit_[r] = 0;
+            if (unit >= UNITS) continue;
+            const uint32_t b = unit * 32 + lane;
+            const uint32_t f = fill[b], i0 = init[b];
+            const uint32_t cap = 0x4000u - (i0 >> 17);
+            const uint32_t u = (int32_t)f < 0 ? cap : ((f - i0) & 0x1FFFFu) >> 1;     // elements staged
+            const uint32_t ru = (u + CH - 1) & ~(uint32_t)(CH - 1);
+            uint32_t at = 0, nfit = 0;
+            if (u) {
+                at = atomicAdd(cursor + b, ru);
+                const uint32_t l = __ldg(base + b + 1);       // end of the bucket in `data`
+                nfit = at >= l ? 0u : min(ru, l - at) / CH;
+            }
+            fill[b] = i0;
+            u_[r] = u; slot_[r] = (i0 & 0x1FFFFu) >> 1; at_[r] = at; nfit_[r] = nfit;
+        }
+        // staging-overflow list: one chunk per element
+        {
+            const uint32_t n_all = s_novf[par], n_ovf = min(n_all, PT_OVF_CAP);
+            if (tid == 0) {
+                s_novf[par ^ 1] = 0;
+                s_stats[0] += n_all;
+                if (n_all > n_ovf) s_stats[1] += n_all - n_ovf;
+            }
+            for (uint32_t i = tid; i < n_ovf; i += PT_THREADS) {
+                const uint32_t code = ovf[i], b = code >> PT_LB;
+                const uint32_t at = atomicAdd(cursor + b, (uint32_t)CH);
+                if (at + CH <= __ldg(base + b + 1)) {
+                    uint32_t w[CH / 2];
+#pragma unroll
+                    for (int q = 0; q < CH / 2; ++q) w[q] = 0xFFFFFFFFu;
+                    w[0] = 0xFFFF0000u | (code & LMASK);
+                    *reinterpret_cast<vec_t *>(data + at) = Chunk<CH>::make(w);
+                } else {
+                    atomicAdd(top + code, 1u);
+                    atomicAdd(&s_stats[1], 1u);
+                }
+            }
+        }
+        // ---- copy the runs: LPB lanes per bucket, one chunk of CH elements per lane and trip ----
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t b0 = (r * WARPS + warp) * 32;
+            if (b0 >= NB) continue;
+#pragma unroll 1
+            for (int sr = 0; sr < 32 / BPS; ++sr) {
+                const int k = sr * BPS + (int)(lane / LPB);
+                const uint32_t u = __shfl_sync(0xffffffffu, u_[r], k);
+                const uint32_t slot = __shfl_sync(0xffffffffu, slot_[r], k);
+                const uint32_t at = __shfl_sync(0xffffffffu, at_[r], k);
+                const uint32_t nfit = __shfl_sync(0xffffffffu, nfit_[r], k);
+                for (uint32_t c = lane % LPB; c * CH < u; c += LPB) {
+                    const vec_t v = *reinterpret_cast<const vec_t *>(stg + 2 * (slot + c * CH));
+                    uint32_t w[CH / 2];
+                    Chunk<CH>::words(v, w);
+                    const uint32_t nv = u - c * CH;            // valid elements of this chunk (>= 1)
+                    if (nv < CH) {
+#pragma unroll
+                        for (int q = 0; q < CH / 2; ++q) {
+                            const int left = (int)nv - 2 * q;      // valid elements in word q
+                            if (left <= 0) w[q] = 0xFFFFFFFFu;
+                            else if (left == 1) w[q] |= 0xFFFF0000u;
+                        }
+                    }
+                    if (c < nfit) {
+                        *reinterpret_cast<vec_t *>(data + at + c * CH) = Chunk<CH>::make(w);
+                    } else {                                   // bucket full: straight to the table
+#pragma unroll
+                        for (int q = 0; q < CH; ++q) {
+                            const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                            if (e != 0xFFFFu) {
+                                atomicAdd(top + (((b0 + k) << PT_LB) | e), 1u);
+                                atomicAdd(&s_stats[1], 1u);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        par ^= 1;
+        G = N;
+    }
+    __syncthreads();
+    if (tid < 4 && s_stats[tid]) atomicAdd(stats + tid, (unsigned long long)s_stats[tid]);
+}
+
+// ---- work items of phase 4: ceil(size_b / BC_ITEM) per bucket ----------------------------------------
+__global__ void k_item_prefix(const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ cursor, uint32_t nb,
+                              uint32_t *__restrict__ item_prefix)
+{
+    // single block; nb <= 1024
+    __shared__ uint32_t s[1025];
     for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
-        const uint32_t sz = bucket_base[b + 1] - bucket_base[b];
+        const uint32_t sz = min(cursor[b], bucket_base[b + 1]) - bucket_base[b];
         s[b] = (sz + BC_ITEM - 1) / BC_ITEM;
     }
     __syncthreads();
@@ -213,11 +393,23 @@ __global__ void k_item_prefix(const uint32_t *__restrict__ bucket_base, uint32_t
     }
 }
 
-// ---- (3) shared-memory histogram of each bucket, added to the top table ------------------------------
+// ---- (4) shared-memory histogram of each bucket, added to the top table ------------------------------
+__device__ __forceinline__ void count1(uint32_t *tab, uint32_t e)
+{
+    if (e != PT_PAD) atomicAdd(&tab[e], 1u);
+}
+__device__ __forceinline__ void count8(uint32_t *tab, const uint4 x)
+{
+    count1(tab, x.x & 0xffffu); count1(tab, x.x >> 16);
+    count1(tab, x.y & 0xffffu); count1(tab, x.y >> 16);
+    count1(tab, x.z & 0xffffu); count1(tab, x.z >> 16);
+    count1(tab, x.w & 0xffffu); count1(tab, x.w >> 16);
+}
+
 __global__ void __launch_bounds__(BC_THREADS)
 k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restrict__ bucket_base,
-               const uint32_t *__restrict__ item_prefix, uint32_t nb, int lb, uint32_t *__restrict__ top,
-               uint32_t *__restrict__ work_counter)
+               const uint32_t *__restrict__ cursor, const uint32_t *__restrict__ item_prefix, uint32_t nb, int lb,
+               uint32_t *__restrict__ top, uint32_t *__restrict__ work_counter)
 {
     extern __shared__ uint32_t tab[];
     __shared__ uint32_t s_item;
@@ -237,39 +429,37 @@ k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restr
         }
         const uint32_t b = lo;
         const uint32_t part = item - item_prefix[b];
+        const uint32_t bend = min(cursor[b], bucket_base[b + 1]);
         const uint32_t beg = bucket_base[b] + part * BC_ITEM;
-        const uint32_t end = min(bucket_base[b + 1], beg + BC_ITEM);
-        // head up to 16-byte alignment, vector body, tail
+        const uint32_t end = min(bend, beg + BC_ITEM);
+        // head up to 16-byte alignment, vector body (two loads in flight per thread), tail
         const uint32_t abeg = min(end, (beg + 7u) & ~7u);
         const uint32_t aend = abeg + ((end - abeg) & ~7u);
-        for (uint32_t i = beg + threadIdx.x; i < abeg; i += BC_THREADS) atomicAdd(&tab[bucket_data[i]], 1u);
+        for (uint32_t i = beg + threadIdx.x; i < abeg; i += BC_THREADS) count1(tab, bucket_data[i]);
         const uint4 *v = reinterpret_cast<const uint4 *>(bucket_data + abeg);
         const uint32_t nv = (aend - abeg) >> 3;
-        for (uint32_t i = threadIdx.x; i < nv; i += BC_THREADS) {
-            const uint4 x = __ldg(v + i);
-            atomicAdd(&tab[x.x & 0xffffu], 1u); atomicAdd(&tab[x.x >> 16], 1u);
-            atomicAdd(&tab[x.y & 0xffffu], 1u); atomicAdd(&tab[x.y >> 16], 1u);
-            atomicAdd(&tab[x.z & 0xffffu], 1u); atomicAdd(&tab[x.z >> 16], 1u);
-            atomicAdd(&tab[x.w & 0xffffu], 1u); atomicAdd(&tab[x.w >> 16], 1u);
+        uint32_t i = threadIdx.x;
+        for (; i + 3 * BC_THREADS < nv; i += 4 * BC_THREADS) {
+            const uint4 x0 = __ldcs(v + i), x1 = __ldcs(v + i + BC_THREADS);
+            const uint4 x2 = __ldcs(v + i + 2 * BC_THREADS), x3 = __ldcs(v + i + 3 * BC_THREADS);
+            count8(tab, x0); count8(tab, x1); count8(tab, x2); count8(tab, x3);
         }
-        for (uint32_t i = aend + threadIdx.x; i < end; i += BC_THREADS) atomicAdd(&tab[bucket_data[i]], 1u);
+        for (; i < nv; i += BC_THREADS) count8(tab, __ldcs(v + i));
+        for (uint32_t j = aend + threadIdx.x; j < end; j += BC_THREADS) count1(tab, bucket_data[j]);
         __syncthreads();
         uint32_t *dst = top + ((uint64_t)b << lb);
-        for (uint32_t i = threadIdx.x; i < bins; i += BC_THREADS) {
-            const uint32_t c = tab[i];
-            if (c) atomicAdd(dst + i, c);
+        for (uint32_t j = threadIdx.x; j < bins; j += BC_THREADS) {
+            const uint32_t c = tab[j];
+            if (c) atomicAdd(dst + j, c);
         }
         __syncthreads();
     }
 }
 
-int swga_exclusive_scan(swga_ctx *ctx, const uint32_t *d_in, uint64_t n, uint32_t *d_out, uint32_t *d_total,
-                        cudaStream_t stream);
-
 int swga_count_partition_supported(uint64_t n_starts, int kmax, int *ok)
 {
     const int pb = 2 * kmax - PT_LB;
-    *ok = !(pb < 1 || pb > PT_MAX_PB || n_starts < (1u << 22) || n_starts >= 0xfff00000ull);
+    *ok = !(pb < PT_MIN_PB || pb > PT_MAX_PB || n_starts < (1u << 22) || n_starts > 0xE0000000ull);
     return SWGA_OK;
 }
 
@@ -285,32 +475,63 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     if (!ok) return SWGA_OK;
     const uint32_t nb = 1u << pb;
     const TableOffs offs = swga_make_offs(kmin, kmax);
-    // workspace: bucket data (2 B per start) + bucket_cnt[nb+2] + cursor[nb] + item_prefix[nb+1] + work counter
-    TRY(swga_ensure(ctx, ctx->bucket_data, (size_t)n_starts * 2 + 64));
-    TRY(swga_ensure(ctx, ctx->bucket_meta, (size_t)(4 * nb + 16) * 4));
-    uint16_t *data = (uint16_t *)ctx->bucket_data.p;
-    uint32_t *base = (uint32_t *)ctx->bucket_meta.p;          // [nb + 1] counts -> exclusive bases (+ total)
-    uint32_t *cursor = base + nb + 2;                          // [nb]
-    uint32_t *item_prefix = cursor + nb;                       // [nb + 1]
-    uint32_t *work = item_prefix + nb + 1;                     // [1]
-    CUDA_TRY(cudaMemsetAsync(base, 0, (size_t)(4 * nb + 16) * 4, stream));
-    const int grid_h = ctx->sm_count * 4;
-    k_bucket_hist<<<grid_h, PT_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, base);
-    TRY(swga_exclusive_scan(ctx, base, nb, base, base + nb, stream));
-    CUDA_TRY(cudaMemcpyAsync(cursor, base, nb * 4, cudaMemcpyDeviceToDevice, stream));
+    // sample: one warp-tile (32 groups = 1024 starts) out of every `stride`, at least ~2^15 groups
+    const uint64_t n_groups = (n_starts + 31) / 32;
+    const uint32_t stride = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, n_groups >> 15));
+    const uint64_t n_sampled = (n_groups / (32ull * stride)) * 32 + std::min<uint64_t>(32, n_groups % (32ull * stride));
+    const uint32_t ratio = (uint32_t)((n_groups + n_sampled - 1) / n_sampled);
+    // upper bound of the layout (sum of estimate + slack over the buckets; Cauchy-Schwarz on the sqrt terms)
+    const double s_tot = (double)n_sampled * 32.0;
     const uint32_t n_tiles = (uint32_t)((n_starts + PT_TILE - 1) / PT_TILE);
-    const size_t smem_p = (size_t)3 * nb * 4 + (size_t)PT_TILE * 4;
-    CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    const int per_sm_p = smem_p <= 100 * 1024 ? 2 : 1;
-    const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * per_sm_p);
-    k_partition<<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, kmax, pb, d_tables, offs, cursor,
-                                                       data, n_tiles);
-    k_item_prefix<<<1, 1024, 0, stream>>>(base, nb, item_prefix);
+    const uint64_t pad = (uint64_t)n_tiles * (PT_CH / 2);      // expected padding per bucket: (PT_CH - 1) / 2 per tile
+    const uint64_t capacity = (uint64_t)((double)n_groups * 32.0 * (17.0 / 16.0) + 8.0 * ratio * sqrt((double)nb * (s_tot + nb)) +
+                                         (1033.0 + (double)pad) * nb + 64.0 * ratio + 4096.0);
+    if (capacity >= 0xFFFFFFF0ull) return SWGA_OK;            // offsets are 32-bit
+    // workspace: bucket data (2 B per slot) + sample[nb] + base[nb+1] + cursor[nb] + init[nb] + item_prefix[nb+1] + work
+    TRY(swga_ensure(ctx, ctx->bucket_data, (size_t)capacity * 2 + 64));
+    TRY(swga_ensure(ctx, ctx->bucket_meta, (size_t)(5 * nb + 16) * 4));
+    uint16_t *data = (uint16_t *)ctx->bucket_data.p;
+    uint32_t *sample = (uint32_t *)ctx->bucket_meta.p;         // [nb]
+    uint32_t *base = sample + nb;                              // [nb + 1]
+    uint32_t *cursor = base + nb + 1;                          // [nb]
+    uint32_t *init = cursor + nb;                              // [nb]
+    uint32_t *item_prefix = init + nb;                         // [nb + 1]
+    uint32_t *work = item_prefix + nb + 1;                     // [1]
+    unsigned long long *stats = (unsigned long long *)(sample + 5 * nb + 4);   // [4] exits taken (swga_count_partition_stats)
+    ctx->part_stats = stats;
+    CUDA_TRY(cudaMemsetAsync(sample, 0, (size_t)(5 * nb + 16) * 4, stream));
+    const int grid_h = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (n_sampled + PT_THREADS - 1) / PT_THREADS);
+    k_bucket_hist<<<grid_h, PT_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
+    k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
+    const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_STAGE * 2;
+    const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 2);
+    if (kmax == 12) {
+        CUDA_TRY(cudaFuncSetAttribute(k_partition<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        k_partition<12><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base, init,
+                                                                cursor, data, n_tiles, stats);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_partition<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        k_partition<11><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base, init,
+                                                                cursor, data, n_tiles, stats);
+    }
+    k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);
     const size_t smem_c = (size_t)4 << PT_LB;
     CUDA_TRY(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    k_bucket_count<<<ctx->sm_count * 3, BC_THREADS, smem_c, stream>>>(data, base, item_prefix, nb, PT_LB,
+    k_bucket_count<<<ctx->sm_count * 3, BC_THREADS, smem_c, stream>>>(data, base, cursor, item_prefix, nb, PT_LB,
                                                                      d_tables + offs.off[kmax], work);
     CUDA_TRY(cudaGetLastError());
     *done = 1;
+    return SWGA_OK;
+}
+
+extern "C" int swga_count_partition_stats(swga_ctx *ctx, uint64_t *h_stats)
+{
+    ARG_CHECK(ctx && h_stats);
+    if (!ctx->part_stats) {
+        memset(h_stats, 0, 4 * sizeof(uint64_t));
+        return SWGA_OK;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(h_stats, ctx->part_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return SWGA_OK;
 }

@@ -154,7 +154,7 @@ def test_properties_at_scale(torch_cuda):
             assert (diff >= 0).all() and int(diff.sum()) == n_rec      # one tail k-mer per record per level
 
 
-@pytest.mark.parametrize("kmin,kmax", [(5, 12), (8, 8), (6, 13), (9, 10)])
+@pytest.mark.parametrize("kmin,kmax", [(5, 12), (8, 11), (11, 11), (12, 12)])
 def test_partitioned_kernel_equals_direct_and_oracle(kmin, kmax, oracle, torch_cuda):
     """The partitioned shared-memory counting path (csrc/count_part.cu) against the direct red.global
     kernel and the oracle, on a genome with N runs, IUPAC bytes and short records (mode A)."""
@@ -181,4 +181,45 @@ def test_partitioned_kernel_equals_direct_and_oracle(kmin, kmax, oracle, torch_c
         _lib.check(lib.swga_ctx_set_count_impl(ctx.h, 0))
     assert np.array_equal(out[1], out[2])
     want = oracle.count_dense_allk(seq, rs, kmin, kmax, mode_b=0)
+    assert np.array_equal(out[2], want)
+
+
+@pytest.mark.parametrize("mode_b", [False, True])
+def test_partitioned_kernel_on_hostile_composition(mode_b, oracle, torch_cuda):
+    """The partitioned path sizes its buckets and its per-tile staging ranges from a strided SAMPLE of the
+    genome (one 1024-start block in every 16 Ki).  This genome is built to make the sample wrong in every
+    way the kernel has an exit for: composition that changes along the genome (staging ranges overflow
+    into the per-tile list), a long two-base repeat (the list overflows too), poly-A / N runs (uniform
+    groups; N -> G in mode B), and a repeat placed only where the sample does not look (global buckets
+    overflow into direct table updates).  Counts must still equal the direct kernel's and the oracle's."""
+    torch = torch_cuda
+    from swga_b200 import _lib, kmers, synth
+    lib, ctx = _lib.load(), _lib.context(0)
+    n = 24_000_000
+    seq = np.concatenate([synth.bases(51, 0, n // 3, 0.15), synth.bases(52, 0, n // 3, 0.80),
+                          synth.bases(53, 0, n - 2 * (n // 3), 0.45)])
+    seq[2_000_000:2_300_000] = np.frombuffer(b"AC" * 150_000, dtype=np.uint8)
+    seq[5_000_000:5_200_000] = ord("A")
+    seq[9_000_000:9_150_000] = ord("N")
+    unit = np.frombuffer(b"ACGTTGCAAGGCTT" * 1200, dtype=np.uint8)
+    pos = np.arange(16_000_000, 23_000_000)
+    hidden = pos[(pos % 16384) >= 1100]                        # never inside a sampled block
+    seq[hidden] = unit[hidden % len(unit)]
+    rs = np.array([0, 7_999_999, 8_000_000, 8_000_010, n], dtype=np.uint64)
+    d = torch.from_numpy(seq).cuda()
+    out = {}
+    try:
+        for impl in (1, 2):
+            _lib.check(lib.swga_ctx_set_count_impl(ctx.h, impl))
+            _, canon = kmers.count_all_device(d, rs, mode_b=mode_b, kmin=5, kmax=12)
+            torch.cuda.synchronize()
+            out[impl] = u32(canon)
+        stats = np.zeros(4, dtype=np.uint64)
+        _lib.check(lib.swga_count_partition_stats(ctx.h, stats.ctypes.data_as(_lib.c_u64p)))
+    finally:
+        _lib.check(lib.swga_ctx_set_count_impl(ctx.h, 0))
+    # every exit of the kernel was taken: staging range full, global bucket full, uniform groups, break groups
+    assert all(int(x) > 0 for x in stats), stats
+    assert np.array_equal(out[1], out[2])
+    want = oracle.count_dense_allk(seq, rs, 5, 12, mode_b=int(mode_b))
     assert np.array_equal(out[2], want)

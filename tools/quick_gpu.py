@@ -26,15 +26,19 @@ def step():
     ev[3].record(); _lib.check(lib.swga_count_finalize(ctx.h, 5, 12, _lib.ptr(fwd), None))
     ev[4].record(); _lib.check(lib.swga_fold_canonical(ctx.h, 5, 12, _lib.ptr(fwd), _lib.ptr(canon), None))
     ev[5].record()
-cfgs = [(1, 0), (2, 0), (0, 0)]
+cfgs = [(1, 0), (2, 0)] if len(sys.argv) < 3 else [(int(sys.argv[2]), 0)]
 for impl, pm in cfgs:
   _lib.check(lib.swga_ctx_set_count_impl(ctx.h, impl));
-  print("impl", impl, "permille", pm)
+  print("impl", impl)
   for i in range(3):
     step(); torch.cuda.synchronize()
     t = [ev[j].elapsed_time(ev[j + 1]) for j in range(5)]
     if i == 2: print("n=%d  zero %.3f  pack %.3f  count %.3f  finalize %.3f  fold %.3f  total %.3f ms  -> %.1f Gbases/s (count alone %.1f G atomics/s)"
           % (n, *t, sum(t), n / sum(t) / 1e6, n / t[2] / 1e6), flush=True)
+  st = np.zeros(4, dtype=np.uint64)
+  _lib.check(lib.swga_count_partition_stats(ctx.h, st.ctypes.data_as(_lib.c_u64p)))
+  print("partition stats [staging-full, bucket-full, uniform groups, break groups]:", st.tolist(), flush=True)
+  print("digest", int(canon.to(torch.int64).sum()), int((canon.to(torch.int64) * torch.arange(words, device="cuda") % 1000003).sum()), flush=True)
 sys.exit(0)
 ms = ctypes.c_float()
 for tw in (1 << 10, 1 << 16, 1 << 20, 1 << 24, 1 << 26):
