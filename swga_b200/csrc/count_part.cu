@@ -30,10 +30,9 @@
 #define PT_MIN_PB 8                                 // kmax = 11
 #define PT_MAX_PB 10                                // kmax = 12
 #define PT_STAGE 52224u                             // uint16 staging slots per tile (102 KB)
-#ifndef PT_CH
-#define PT_CH 4                                     // elements per chunk: bucket runs are stored in whole chunks,
-#endif                                              // padded with PT_PAD (ignored by k_bucket_count)
-#define PT_PAD 0xFFFFu
+#define PT_CH 8                                     // bucket runs are stored in whole 16-byte chunks of 8 elements,
+#define PT_PAD_WORD 0x40004000u                     // padded with values 0x4000 | r (r < PT_PAD_BINS), which land in
+#define PT_PAD_BINS 64                              // dump bins behind k_bucket_count's 2^14-bin table
 #define PT_OVF_CAP 512u                             // staging-overflow list entries per tile
 #define PT_ADD ((1u << 17) + 2u)                    // one element: guard += 1, byte address += 2
 #define BC_THREADS 512
@@ -197,19 +196,6 @@ k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n
 }
 
 // ---- (3) scatter the low bits into prefix buckets --------------------------------------------------
-// A chunk of PT_CH staged elements (uint16 each) as one vector.
-template <int CH> struct Chunk;
-template <> struct Chunk<4> {
-    typedef uint2 vec;
-    static __device__ __forceinline__ void words(const vec &v, uint32_t *w) { w[0] = v.x; w[1] = v.y; }
-    static __device__ __forceinline__ vec make(const uint32_t *w) { return make_uint2(w[0], w[1]); }
-};
-template <> struct Chunk<8> {
-    typedef uint4 vec;
-    static __device__ __forceinline__ void words(const vec &v, uint32_t *w) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-    static __device__ __forceinline__ vec make(const uint32_t *w) { return make_uint4(w[0], w[1], w[2], w[3]); }
-};
-
 template <int KMAX>
 __global__ void __launch_bounds__(PT_THREADS, 2)
 k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
@@ -219,10 +205,8 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
 {
     constexpr int PB = 2 * KMAX - PT_LB, SH = 32 - 2 * KMAX;
     constexpr uint32_t NB = 1u << PB, LMASK = (1u << PT_LB) - 1u;
-    constexpr int CH = PT_CH, LPB = 32 / CH, BPS = 32 / LPB;   // lanes per bucket, buckets per sub-round
     constexpr int WARPS = PT_THREADS / 32, UNITS = NB / 32;      // a unit = 32 buckets, one per lane
     constexpr int ROUNDS = (UNITS + WARPS - 1) / WARPS;        // units per warp
-    typedef typename Chunk<CH>::vec vec_t;
     extern __shared__ __align__(16) uint32_t sm[];
     uint32_t *fill = sm;                                       // [NB] (guard << 17) | byte address of the next slot
     uint32_t *init = fill + NB;                                // [NB] value of fill at the start of a tile
@@ -234,6 +218,18 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     uint32_t *__restrict__ top = tables + offs.off[KMAX];
     if (tid < 4) s_stats[tid] = 0;
 
+    // The staging area always holds padding wherever no element of the current tile was staged: filled
+    // here, and every chunk copied out is replaced by padding.  Pad values are 0x4000 | r, r < 64: they
+    // land in k_bucket_count's dump bins, spread so that they do not pile up on one shared-memory word.
+    uint4 padv;
+    {
+        const uint32_t r0 = lane * 8;
+        padv.x = PT_PAD_WORD | ((r0 + 0) & 63) | (((r0 + 1) & 63) << 16);
+        padv.y = PT_PAD_WORD | ((r0 + 2) & 63) | (((r0 + 3) & 63) << 16);
+        padv.z = PT_PAD_WORD | ((r0 + 4) & 63) | (((r0 + 5) & 63) << 16);
+        padv.w = PT_PAD_WORD | ((r0 + 6) & 63) | (((r0 + 7) & 63) << 16);
+    }
+    for (uint32_t i = tid; i < PT_STAGE / 8; i += PT_THREADS) reinterpret_cast<uint4 *>(stg)[i] = padv;
     for (uint32_t i = tid; i < NB; i += PT_THREADS) {
         const uint32_t v = init_g[i];
         init[i] = v;
@@ -279,26 +275,25 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
             if (g * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
         }
         __syncthreads();
-        // ---- per warp: reserve the global range of the runs of its buckets, re-arm their counters ----
-        uint32_t u_[ROUNDS], slot_[ROUNDS], at_[ROUNDS], nfit_[ROUNDS];
+        // ---- per warp: reserve the global range of the runs of its buckets (whole chunks of 8), re-arm ----
+        uint32_t A_[ROUNDS], at_[ROUNDS];                      // A = staged | first slot << 15 | does-not-fit << 31
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t unit = r * WARPS + warp;
-            u_[r] = slot_[r] = at_[r] = nfit_[r] = 0;
+            A_[r] = at_[r] = 0;
             if (unit >= UNITS) continue;
             const uint32_t b = unit * 32 + lane;
             const uint32_t f = fill[b], i0 = init[b];
-            const uint32_t cap = 0x4000u - (i0 >> 17);
-            const uint32_t u = (int32_t)f < 0 ? cap : ((f - i0) & 0x1FFFFu) >> 1;     // elements staged
-            const uint32_t ru = (u + CH - 1) & ~(uint32_t)(CH - 1);
-            uint32_t at = 0, nfit = 0;
+            const uint32_t u = (int32_t)f < 0 ? 0x4000u - (i0 >> 17) : ((f - i0) & 0x1FFFFu) >> 1;   // elements staged
+            const uint32_t ru = (u + 7u) & ~7u;
+            uint32_t at = 0, part = 0;
             if (u) {
                 at = atomicAdd(cursor + b, ru);
-                const uint32_t l = __ldg(base + b + 1);       // end of the bucket in `data`
-                nfit = at >= l ? 0u : min(ru, l - at) / CH;
+                part = at + ru > __ldg(base + b + 1);          // beyond the end of the bucket in `data`
             }
             fill[b] = i0;
-            u_[r] = u; slot_[r] = (i0 & 0x1FFFFu) >> 1; at_[r] = at; nfit_[r] = nfit;
+            A_[r] = u | ((i0 & 0x1FFFFu) >> 1) << 15 | part << 31;
+            at_[r] = at;
         }
         // staging-overflow list: one chunk per element
         {
@@ -310,53 +305,55 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
             }
             for (uint32_t i = tid; i < n_ovf; i += PT_THREADS) {
                 const uint32_t code = ovf[i], b = code >> PT_LB;
-                const uint32_t at = atomicAdd(cursor + b, (uint32_t)CH);
-                if (at + CH <= __ldg(base + b + 1)) {
-                    uint32_t w[CH / 2];
-#pragma unroll
-                    for (int q = 0; q < CH / 2; ++q) w[q] = 0xFFFFFFFFu;
-                    w[0] = 0xFFFF0000u | (code & LMASK);
-                    *reinterpret_cast<vec_t *>(data + at) = Chunk<CH>::make(w);
+                const uint32_t at = atomicAdd(cursor + b, 8u);
+                if (at + 8u <= __ldg(base + b + 1)) {
+                    uint4 v = padv;
+                    v.x = (v.x & 0xFFFF0000u) | (code & LMASK);
+                    *reinterpret_cast<uint4 *>(data + at) = v;
                 } else {
                     atomicAdd(top + code, 1u);
                     atomicAdd(&s_stats[1], 1u);
                 }
             }
         }
-        // ---- copy the runs: LPB lanes per bucket, one chunk of CH elements per lane and trip ----
+        // ---- copy the runs: 4 lanes per bucket, one 16-byte chunk per lane and trip; leave padding behind ----
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t b0 = (r * WARPS + warp) * 32;
             if (b0 >= NB) continue;
-#pragma unroll 1
-            for (int sr = 0; sr < 32 / BPS; ++sr) {
-                const int k = sr * BPS + (int)(lane / LPB);
-                const uint32_t u = __shfl_sync(0xffffffffu, u_[r], k);
-                const uint32_t slot = __shfl_sync(0xffffffffu, slot_[r], k);
+#pragma unroll
+            for (int sr = 0; sr < 4; ++sr) {
+                const int k = sr * 8 + (int)(lane >> 2);
+                const uint32_t A = __shfl_sync(0xffffffffu, A_[r], k);
                 const uint32_t at = __shfl_sync(0xffffffffu, at_[r], k);
-                const uint32_t nfit = __shfl_sync(0xffffffffu, nfit_[r], k);
-                for (uint32_t c = lane % LPB; c * CH < u; c += LPB) {
-                    const vec_t v = *reinterpret_cast<const vec_t *>(stg + 2 * (slot + c * CH));
-                    uint32_t w[CH / 2];
-                    Chunk<CH>::words(v, w);
-                    const uint32_t nv = u - c * CH;            // valid elements of this chunk (>= 1)
-                    if (nv < CH) {
-#pragma unroll
-                        for (int q = 0; q < CH / 2; ++q) {
-                            const int left = (int)nv - 2 * q;      // valid elements in word q
-                            if (left <= 0) w[q] = 0xFFFFFFFFu;
-                            else if (left == 1) w[q] |= 0xFFFF0000u;
-                        }
+                const uint32_t u = A & 0x7FFFu;
+                uint32_t cc = (lane & 3u) * 8u;                // first element of this lane's chunk
+                unsigned char *sp = stg + 2u * ((A >> 15) & 0xFFFFu) + 2u * cc;
+                uint16_t *gp = data + at + cc;
+                if ((int32_t)A >= 0) {
+#pragma unroll 1
+                    for (; cc < u; cc += 32u, sp += 64, gp += 32) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(sp);
+                        *reinterpret_cast<uint4 *>(sp) = padv;
+                        *reinterpret_cast<uint4 *>(gp) = v;
                     }
-                    if (c < nfit) {
-                        *reinterpret_cast<vec_t *>(data + at + c * CH) = Chunk<CH>::make(w);
-                    } else {                                   // bucket full: straight to the table
+                } else {                                       // the run crosses the end of its bucket
+                    const uint32_t l = __ldg(base + b0 + k + 1);
+#pragma unroll 1
+                    for (; cc < u; cc += 32u, sp += 64, gp += 32) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(sp);
+                        *reinterpret_cast<uint4 *>(sp) = padv;
+                        if (at + cc + 8u <= l) {
+                            *reinterpret_cast<uint4 *>(gp) = v;
+                        } else {                               // straight to the table
+                            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int q = 0; q < CH; ++q) {
-                            const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-                            if (e != 0xFFFFu) {
-                                atomicAdd(top + (((b0 + k) << PT_LB) | e), 1u);
-                                atomicAdd(&s_stats[1], 1u);
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                                if (e <= LMASK) {
+                                    atomicAdd(top + (((b0 + k) << PT_LB) | e), 1u);
+                                    atomicAdd(&s_stats[1], 1u);
+                                }
                             }
                         }
                     }
@@ -396,7 +393,7 @@ __global__ void k_item_prefix(const uint32_t *__restrict__ bucket_base, const ui
 // ---- (4) shared-memory histogram of each bucket, added to the top table ------------------------------
 __device__ __forceinline__ void count1(uint32_t *tab, uint32_t e)
 {
-    if (e != PT_PAD) atomicAdd(&tab[e], 1u);
+    atomicAdd(&tab[e], 1u);                                    // padding (>= 2^14) goes to the dump bins
 }
 __device__ __forceinline__ void count8(uint32_t *tab, const uint4 x)
 {
@@ -417,7 +414,7 @@ k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restr
     const uint32_t n_items = item_prefix[nb];
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1u);
-        for (uint32_t i = threadIdx.x; i < bins; i += BC_THREADS) tab[i] = 0;
+        for (uint32_t i = threadIdx.x; i < bins + PT_PAD_BINS; i += BC_THREADS) tab[i] = 0;
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_items) break;
@@ -515,7 +512,7 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
                                                                 cursor, data, n_tiles, stats);
     }
     k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);
-    const size_t smem_c = (size_t)4 << PT_LB;
+    const size_t smem_c = ((size_t)4 << PT_LB) + 4 * PT_PAD_BINS;
     CUDA_TRY(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     k_bucket_count<<<ctx->sm_count * 3, BC_THREADS, smem_c, stream>>>(data, base, cursor, item_prefix, nb, PT_LB,
                                                                      d_tables + offs.off[kmax], work);
