@@ -61,6 +61,27 @@ __device__ __forceinline__ Group load_group(const uint32_t *__restrict__ packed,
     return r;
 }
 
+// Same, through volatile asm loads: the compiler may neither sink them to the first use nor re-issue them
+// there (a plain __ldg of read-only data is rematerialised, which turns a prefetch into a stall).
+__device__ __forceinline__ Group load_group_pinned(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
+                                                   uint64_t g, uint64_t n_starts, int kmax)
+{
+    Group r;
+    r.fast = false;
+    r.w0 = r.w1 = r.w2 = 0;
+    const uint64_t p0 = g * 32;
+    if (p0 >= n_starts) return r;
+    uint32_t b0, b1;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(packed + 2 * g));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w2) : "l"(packed + 2 * g + 2));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b0) : "l"(brk + g));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b1) : "l"(brk + g + 1));
+    const int need = kmax - 2;
+    const uint32_t tail = need > 0 ? (b1 >> (32 - need)) : 0u;
+    r.fast = (p0 + 32 <= n_starts) && ((b0 | tail) == 0u);
+    return r;
+}
+
 // the 16 bases starting at offset o (0..31) of the group, first base in bits 31:30
 __device__ __forceinline__ uint32_t window(const Group &g, int o)
 {
@@ -245,7 +266,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
         Group N;                                               // next tile's group: in flight during this tile
         N.fast = false;
         N.w0 = N.w1 = N.w2 = 0;
-        if (tile + gridDim.x < n_tiles) N = load_group(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, n_starts, KMAX);
+        if (tile + gridDim.x < n_tiles) N = load_group_pinned(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, n_starts, KMAX);
         // ---- every element takes its staging slot ----
         if (G.fast) {
             if (uniform_group(G, KMAX)) {
@@ -258,8 +279,10 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                     const uint32_t W = window(G, o);
                     const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
                     const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
+                    // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on
+                    // a 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
                     if ((int32_t)old >= 0)
-                        *reinterpret_cast<uint16_t *>(stg + (old & 0x1FFFFu)) = (uint16_t)((W >> SH) & LMASK);
+                        *reinterpret_cast<uint16_t *>(stg + ((old & 0x1FFFFu) ^ ((boff >> 1) & 0xEu))) = (uint16_t)((W >> SH) & LMASK);
                     full = __funnelshift_l(old, full, 1);
                 }
                 while (full) {                                 // rare: the tile's composition is off the sample's
