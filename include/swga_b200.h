@@ -126,6 +126,12 @@ int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *d_tables, v
  * their global bucket full (added to the table directly), [2] = single-base-run groups of 32 starts,
  * [3] = groups that took the direct path because they touch a break.  All zero when the direct kernel ran. */
 int swga_count_partition_stats(swga_ctx *ctx, uint64_t *h_stats);
+/* Per-kernel timing of the partitioned swga_count_accumulate (bench.py's roofline of the dominant kernel):
+ * with timing on, CUDA events are recorded on the call's stream between its kernels; swga_count_stage_ms
+ * waits for the last call and returns milliseconds of {sample histogram + layout, k_partition,
+ * k_item_prefix + k_bucket_count} (zeros when the direct kernel ran). */
+int swga_ctx_set_stage_timing(swga_ctx *ctx, int on);
+int swga_count_stage_ms(swga_ctx *ctx, float *h_ms);
 int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd,
                         uint32_t *d_canon, void *stream);
 

@@ -76,6 +76,8 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     delete c;

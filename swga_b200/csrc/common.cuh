@@ -51,6 +51,9 @@ struct swga_ctx {
     DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp, bucket_data, bucket_meta;
     uint32_t score_sort_cap = 4096;                    // raw sites per set up to which k_score_sort is used (0 = never)
     unsigned long long *part_stats = nullptr;          // inside bucket_meta: exits taken by the last partitioned count
+    int stage_timing = 0;                              // record events between the kernels of the partitioned count
+    cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    int stage_valid = 0;
     int count_impl = 0;                                // 0 = auto, 1 = direct red.global kernel, 2 = partitioned
 };
 

@@ -323,6 +323,7 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
         }
     }
     ctx->part_stats = nullptr;
+    ctx->stage_valid = 0;
     k_count<<<grid_for((n_starts + 31) / 32, 256), 256, 0, st>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables, offs);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;

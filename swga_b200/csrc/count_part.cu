@@ -61,25 +61,33 @@ __device__ __forceinline__ Group load_group(const uint32_t *__restrict__ packed,
     return r;
 }
 
-// Same, through volatile asm loads: the compiler may neither sink them to the first use nor re-issue them
-// there (a plain __ldg of read-only data is rematerialised, which turns a prefetch into a stall).
-__device__ __forceinline__ Group load_group_pinned(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
-                                                   uint64_t g, uint64_t n_starts, int kmax)
+// The group of the NEXT tile, fetched a whole tile ahead.  Volatile asm loads: the compiler may neither sink
+// them to the first use nor re-issue them there (a plain __ldg of read-only data is rematerialised, which
+// turns a prefetch into a stall); nothing is computed from the values until finish_group().
+struct RawGroup {
+    uint32_t w0, w1, w2, b0, b1;
+};
+__device__ __forceinline__ RawGroup prefetch_group(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
+                                                   uint64_t g, uint64_t n_starts)
 {
-    Group r;
-    r.fast = false;
+    RawGroup r;
     r.w0 = r.w1 = r.w2 = 0;
-    const uint64_t p0 = g * 32;
-    if (p0 >= n_starts) return r;
-    uint32_t b0, b1;
+    r.b0 = r.b1 = 0xffffffffu;
+    if (g * 32 >= n_starts) return r;
     asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(packed + 2 * g));
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w2) : "l"(packed + 2 * g + 2));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b0) : "l"(brk + g));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b1) : "l"(brk + g + 1));
-    const int need = kmax - 2;
-    const uint32_t tail = need > 0 ? (b1 >> (32 - need)) : 0u;
-    r.fast = (p0 + 32 <= n_starts) && ((b0 | tail) == 0u);
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.b0) : "l"(brk + g));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.b1) : "l"(brk + g + 1));
     return r;
+}
+__device__ __forceinline__ Group finish_group(const RawGroup &r, uint64_t g, uint64_t n_starts, int kmax)
+{
+    Group G;
+    G.w0 = r.w0; G.w1 = r.w1; G.w2 = r.w2;
+    const int need = kmax - 2;
+    const uint32_t tail = need > 0 ? (r.b1 >> (32 - need)) : 0u;
+    G.fast = (g * 32 + 32 <= n_starts) && ((r.b0 | tail) == 0u);
+    return G;
 }
 
 // the 16 bases starting at offset o (0..31) of the group, first base in bits 31:30
@@ -260,13 +268,12 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     __syncthreads();
 
     uint32_t par = 0;
-    Group G = load_group(packed, brk, (uint64_t)blockIdx.x * PT_THREADS + tid, n_starts, KMAX);
+    RawGroup R = prefetch_group(packed, brk, (uint64_t)blockIdx.x * PT_THREADS + tid, n_starts);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t g = (uint64_t)tile * PT_THREADS + tid;
-        Group N;                                               // next tile's group: in flight during this tile
-        N.fast = false;
-        N.w0 = N.w1 = N.w2 = 0;
-        if (tile + gridDim.x < n_tiles) N = load_group_pinned(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, n_starts, KMAX);
+        const Group G = finish_group(R, g, n_starts, KMAX);
+        // next tile's group: in flight during this tile (past the last tile: past n_starts, nothing is loaded)
+        R = prefetch_group(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, tile + gridDim.x < n_tiles ? n_starts : 0);
         // ---- every element takes its staging slot ----
         if (G.fast) {
             if (uniform_group(G, KMAX)) {
@@ -385,7 +392,6 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
         }
         __syncthreads();
         par ^= 1;
-        G = N;
     }
     __syncthreads();
     if (tid < 4 && s_stats[tid]) atomicAdd(stats + tid, (unsigned long long)s_stats[tid]);
@@ -520,9 +526,16 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     unsigned long long *stats = (unsigned long long *)(sample + 5 * nb + 4);   // [4] exits taken (swga_count_partition_stats)
     ctx->part_stats = stats;
     CUDA_TRY(cudaMemsetAsync(sample, 0, (size_t)(5 * nb + 16) * 4, stream));
+    const bool timing = ctx->stage_timing != 0;
+    if (timing) {
+        for (int i = 0; i < 4; ++i)
+            if (!ctx->ev_stage[i]) CUDA_TRY(cudaEventCreate(&ctx->ev_stage[i]));
+        CUDA_TRY(cudaEventRecord(ctx->ev_stage[0], stream));
+    }
     const int grid_h = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (n_sampled + PT_THREADS - 1) / PT_THREADS);
     k_bucket_hist<<<grid_h, PT_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
     k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
+    if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[1], stream));
     const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_STAGE * 2;
     const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 2);
     if (kmax == 12) {
@@ -534,12 +547,17 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
         k_partition<11><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base, init,
                                                                 cursor, data, n_tiles, stats);
     }
+    if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[2], stream));
     k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);
     const size_t smem_c = ((size_t)4 << PT_LB) + 4 * PT_PAD_BINS;
     CUDA_TRY(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     k_bucket_count<<<ctx->sm_count * 3, BC_THREADS, smem_c, stream>>>(data, base, cursor, item_prefix, nb, PT_LB,
                                                                      d_tables + offs.off[kmax], work);
     CUDA_TRY(cudaGetLastError());
+    if (timing) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_stage[3], stream));
+        ctx->stage_valid = 1;
+    }
     *done = 1;
     return SWGA_OK;
 }
@@ -553,5 +571,23 @@ extern "C" int swga_count_partition_stats(swga_ctx *ctx, uint64_t *h_stats)
     }
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(h_stats, ctx->part_stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SWGA_OK;
+}
+
+extern "C" int swga_ctx_set_stage_timing(swga_ctx *ctx, int on)
+{
+    ARG_CHECK(ctx);
+    ctx->stage_timing = on ? 1 : 0;
+    ctx->stage_valid = 0;
+    return SWGA_OK;
+}
+
+extern "C" int swga_count_stage_ms(swga_ctx *ctx, float *h_ms)
+{
+    ARG_CHECK(ctx && h_ms);
+    h_ms[0] = h_ms[1] = h_ms[2] = 0.f;
+    if (!ctx->stage_timing || !ctx->stage_valid) return SWGA_OK;
+    CUDA_TRY(cudaEventSynchronize(ctx->ev_stage[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(h_ms + i, ctx->ev_stage[i], ctx->ev_stage[i + 1]));
     return SWGA_OK;
 }
