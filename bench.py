@@ -189,6 +189,43 @@ class ClockSampler(threading.Thread):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated (first touch
+    then places the buffers on the GPU's NUMA node): with 8 ranks copying at once, buffers on the far
+    socket cap the aggregate H2D rate.  Best effort; returns the node or None."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        h = None
+        for pre in ("GPU-", ""):
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID((pre + uuid).encode())
+                break
+            except Exception:
+                h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        with open(base + "/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        with open(base + "/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -202,9 +239,22 @@ def run_b200_arm(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        td.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first collective: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            td.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib, ctx = _lib.load(), _lib.context(local)
     P = _lib.ptr
 
@@ -420,6 +470,24 @@ def run_b200_arm(args):
         same = bool(torch.equal(h_canon_bg.to(dev), bg.canon))
         e2e["tables_equal_device_path"] = same
 
+    # ---- size-independent parity properties of the full-size tables (no CPU oracle at 3.1 Gbp) ----
+    props = None
+    if world == 1:
+        step()
+        torch.cuda.synchronize()
+        ok = True
+        lens = np.diff(synth.equal_records(n_bg, bg_nrec).astype(np.int64))
+        for k in range(KMIN, KMAX + 1):
+            o0, o1 = int(lib.swga_table_offset(KMIN, k)), int(lib.swga_table_offset(KMIN, k + 1))
+            expect = int(np.maximum(0, lens - k + 1).sum())
+            ok &= int(bg.fwd[o0:o1].sum(dtype=torch.int64)) == expect          # every window counted once
+            ok &= int(bg.canon[o0:o1].sum(dtype=torch.int64)) == expect        # fold loses nothing
+            if k < KMAX:                                                       # table k = marginal of k+1 + one tail per record
+                up = bg.fwd[o1:o1 + 4 ** (k + 1)].view(-1, 4).sum(1, dtype=torch.int64)
+                diff = bg.fwd[o0:o1].to(torch.int64) - up
+                ok &= bool((diff >= 0).all()) and int(diff.sum()) == bg_nrec
+        props = {"bg_tables_sum_and_marginals_ok": bool(ok)}
+
     scoring = None
     if rank == 0 and not args.no_extras:
         try:
@@ -443,8 +511,8 @@ def run_b200_arm(args):
                        "kmin": KMIN, "kmax": KMAX, "sharding": "bg contiguous chunks + 11-base halo, fg replicated"
                        if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
             "roofline": roofline, "path_roofline": path, "atomic": atomic, "cpu_baseline": cpu, "e2e": e2e,
-            "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps,
-            "scoring": scoring,
+            "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps, "numa_node": numa,
+            "scoring": scoring, "full_size_properties": props,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
