@@ -21,7 +21,9 @@
 
 #define SC_THREADS 512
 #define SC_WARPS (SC_THREADS / 32)
-#define SC_TILE_SHIFT 19                                   // 2^19 positions per tile = 1024 per thread
+#define SC_TILE_SHIFT 19                                   // k_score: 2^19 positions per tile = 1024 per thread
+#define DT_SHIFT 13                                        // tile offsets (toff) and k_score_dense: 2^13 positions per tile
+#define SC_FINE_PER_TILE (1u << (SC_TILE_SHIFT - DT_SHIFT)) // fine tiles per k_score tile
 #define SC_L0_WORDS ((1u << SC_TILE_SHIFT) / 32)           // 16384
 #define SC_L0_PHYS (SC_L0_WORDS + SC_L0_WORDS / 32)        // padded: phys(w) = w + (w >> 5)
 #define SC_L1_WORDS (SC_L0_WORDS / 32)                     // 512 == SC_THREADS
@@ -29,7 +31,7 @@
 
 struct ScoreArgs {
     const uint32_t *sites;       // concatenated sorted-unique site lists (linear coordinates)
-    const uint32_t *toff;        // [n_lists][n_tiles + 1] tile offsets into sites
+    const uint32_t *toff;        // [n_lists][n_tiles + 1] offsets into sites of the tiles of 2^DT_SHIFT positions
     uint32_t n_tiles;
     uint32_t bounds_list;        // id of the list holding every record's first and last position
     const int32_t *sets;         // [S][max_m] list ids, -1 padded
@@ -131,11 +133,12 @@ k_score(ScoreArgs a)
         unsigned long long sumsq = 0;
         uint32_t carry = 0;                                // (last position so far) + 1; 0 = none
 
-        for (uint32_t t = 0; t < a.n_tiles; ++t) {
+        const uint32_t n_coarse = (a.n_tiles + SC_FINE_PER_TILE - 1) / SC_FINE_PER_TILE;
+        for (uint32_t t = 0; t < n_coarse; ++t) {
             if (tid < nl) {
-                const uint32_t *row = a.toff + (uint64_t)s_list[tid] * (a.n_tiles + 1) + t;
-                s_lo[tid] = row[0];
-                s_hi[tid] = row[1];
+                const uint32_t *row = a.toff + (uint64_t)s_list[tid] * (a.n_tiles + 1);
+                s_lo[tid] = row[t * SC_FINE_PER_TILE];
+                s_hi[tid] = row[min(a.n_tiles, (t + 1) * SC_FINE_PER_TILE)];
             }
             __syncthreads();
             uint32_t total = 0;
@@ -290,6 +293,334 @@ k_score(ScoreArgs a)
         }
         __syncthreads();
         if (!a.work) break;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Dense sets: one WARP per fine tile of 2^13 positions, no CTA-wide barrier inside a set.  Every warp owns
+// a contiguous range of tiles and a private 1 KB bitmap: (1) the lanes read their lists' segment bounds
+// of the tile, (2) every site sets one bit, (3) each lane takes 8 bitmap words, the set bits are
+// COMPACTED into a warp-private list of tile-relative positions (ascending), (4) the gaps are taken
+// from the list with all lanes busy.  The last position of a tile is carried in a register to the next
+// tile of the warp; the gaps between the ranges of two warps are added once per set.  Statistics as in
+// k_score (exact integers, Gini from the shared gap histogram).
+// ------------------------------------------------------------------------------------------------
+#define DT_THREADS 1024
+#define DT_WARPS (DT_THREADS / 32)
+#define DT_WORDS ((1u << DT_SHIFT) / 32)                   // 256 bitmap words per warp
+#define DT_LIST_CAP 512u                                   // compact list entries per warp (uint16)
+#define DT_MAXL 12                                         // lists whose first 32 sites per tile are prefetched
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce_dt(T v, Op op, T ident, T *scratch /* DT_WARPS + 1 */)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T w = threadIdx.x < DT_WARPS ? scratch[threadIdx.x] : ident;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, d));
+        if (threadIdx.x == 0) scratch[DT_WARPS] = w;
+    }
+    __syncthreads();
+    return scratch[DT_WARPS];
+}
+
+// A read-only load the compiler may neither sink to its first use nor re-issue there (prefetch into registers).
+__device__ __forceinline__ uint32_t ld_pinned(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+struct GapAcc {
+    uint32_t cnt, maxgap;
+    unsigned long long sumsq;
+};
+__device__ __forceinline__ void add_gap(GapAcc &g, uint32_t gap, uint32_t *hist, uint32_t hist_bins)
+{
+    ++g.cnt;
+    g.sumsq += (unsigned long long)gap * gap;
+    g.maxgap = max(g.maxgap, gap);
+    if (gap < hist_bins) atomicAdd(&hist[gap], 1u);
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+k_score_dense(ScoreArgs a)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *bm_all = smem;                                               // [DT_WARPS][DT_WORDS]
+    uint16_t *cl_all = reinterpret_cast<uint16_t *>(bm_all + DT_WARPS * DT_WORDS);   // [DT_WARPS][DT_LIST_CAP]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(cl_all + DT_WARPS * DT_LIST_CAP);  // [a.hist_bins]
+    __shared__ uint32_t s_list[SC_MAX_LISTS];
+    __shared__ uint32_t s_nlists, s_set;
+    __shared__ uint32_t s_first[DT_WARPS], s_last[DT_WARPS];              // (position + 1) of the first / last site of a warp's range
+    __shared__ uint32_t s_red32[DT_WARPS + 1], s_scan[DT_WARPS + 1];
+    __shared__ unsigned long long s_red64[DT_WARPS + 1];
+    __shared__ GapAcc s_cross;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *bm = bm_all + warp * DT_WORDS;
+    uint16_t *cl = cl_all + warp * DT_LIST_CAP;
+    for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
+    for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t tpw = (a.n_tiles + DT_WARPS - 1) / DT_WARPS;            // tiles per warp
+    for (;;) {
+        if (tid == 0) s_set = atomicAdd(a.work + 1, 1u);
+        __syncthreads();
+        if (s_set >= *a.n_ids) break;
+        const uint32_t s = a.ids[s_set];
+        if (tid == 0) {
+            uint32_t n = 0;
+            for (uint32_t j = 0; j < a.max_m && n < SC_MAX_LISTS - 1; ++j) {
+                const int32_t id = a.sets[(uint64_t)s * a.max_m + j];
+                if (id >= 0) s_list[n++] = (uint32_t)id;
+            }
+            s_list[n++] = a.bounds_list;
+            s_nlists = n;
+        }
+        __syncthreads();
+        const uint32_t nl = s_nlists;
+        const uint32_t *row = a.toff + (uint64_t)s_list[lane < nl ? lane : 0] * (a.n_tiles + 1);
+
+        GapAcc acc;
+        acc.cnt = 0; acc.maxgap = 0; acc.sumsq = 0;
+        uint32_t carry = 0, first = 0;                                     // (position + 1); 0 = none yet
+        const uint32_t t0 = min(a.n_tiles, warp * tpw), t1 = min(a.n_tiles, t0 + tpw);
+        // Software pipeline over the warp's tiles: the segment bounds are read two tiles ahead and the first 32
+        // sites of every list of tile t + 1 are loaded while tile t is processed (one L2 latency per tile
+        // instead of one per list).
+        uint32_t b0 = 0, b1 = 0, b2 = 0;                                   // row[t], row[t + 1], row[t + 2] of my list
+        if (lane < nl && t0 < t1) {
+            b0 = row[t0];
+            b1 = row[min(a.n_tiles, t0 + 1)];
+            b2 = row[min(a.n_tiles, t0 + 2)];
+        }
+        uint32_t pv[DT_MAXL];                                              // sites of the current tile, list l, index `lane`
+#pragma unroll
+        for (int l = 0; l < DT_MAXL; ++l) {
+            const uint32_t lo_l = __shfl_sync(0xffffffffu, b0, l), len_l = __shfl_sync(0xffffffffu, b1 - b0, l);
+            pv[l] = lane < len_l ? ld_pinned(a.sites + lo_l + lane) : 0xffffffffu;
+        }
+        for (uint32_t t = t0; t < t1; ++t) {
+            const uint32_t lo = b0, len = b1 - b0;
+            // next tile: bounds are here already; its sites and the bounds after it start their trip now
+            uint32_t pn[DT_MAXL];
+#pragma unroll
+            for (int l = 0; l < DT_MAXL; ++l) {
+                const uint32_t lo_l = __shfl_sync(0xffffffffu, b1, l), len_l = __shfl_sync(0xffffffffu, b2 - b1, l);
+                pn[l] = (t + 1 < t1 && lane < len_l) ? ld_pinned(a.sites + lo_l + lane) : 0xffffffffu;
+            }
+            const uint32_t b3 = (lane < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
+            const uint32_t tile_base = t << DT_SHIFT;
+            const uint32_t any = __reduce_add_sync(0xffffffffu, len);
+            const uint32_t longest = __reduce_max_sync(0xffffffffu, len);
+            if (any) {
+            // ---- (2) one bit per site ----
+#pragma unroll
+            for (int l = 0; l < DT_MAXL; ++l) {
+                if (pv[l] != 0xffffffffu) {
+                    const uint32_t p = pv[l] - tile_base;
+                    atomicOr(&bm[p >> 5], 1u << (p & 31));
+                }
+            }
+            if (longest > 32 || nl > DT_MAXL) {                            // what the prefetch does not cover
+                for (uint32_t l = 0; l < nl; ++l) {
+                    const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
+                    for (uint32_t i = (l < DT_MAXL ? 32u : 0u) + lane; i < len_l; i += 32) {
+                        const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
+                        atomicOr(&bm[p >> 5], 1u << (p & 31));
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- (3) my 8 words; count, scan, compact ----
+            uint32_t w[8];
+            {
+                uint4 *bm4 = reinterpret_cast<uint4 *>(bm) + 2 * lane;
+                const uint4 x = bm4[0], y = bm4[1];
+                bm4[0] = make_uint4(0, 0, 0, 0);
+                bm4[1] = make_uint4(0, 0, 0, 0);
+                w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+            }
+            uint32_t c = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c += __popc(w[q]);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += o;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total <= DT_LIST_CAP) {
+                uint32_t idx = incl - c;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t v = w[q];
+                    const uint32_t wb = (lane * 8 + q) * 32;
+                    while (v) {
+                        cl[idx++] = (uint16_t)(wb + __ffs(v) - 1);
+                        v &= v - 1;
+                    }
+                }
+                __syncwarp();
+                // ---- (4) gaps, all lanes busy ----
+                for (uint32_t j = lane; j < total; j += 32) {
+                    const uint32_t cur = tile_base + cl[j];
+                    const uint32_t prev1 = j ? tile_base + cl[j - 1] + 1 : carry;
+                    if (prev1) {
+                        const uint32_t gap = cur - (prev1 - 1);
+                        add_gap(acc, gap, hist, a.hist_bins);
+                        if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
+                    } else {
+                        first = cur + 1;
+                    }
+                }
+                carry = tile_base + cl[total - 1] + 1;
+                __syncwarp();
+            } else {
+                // more distinct sites than the list holds: each lane walks its own bits; its predecessor is
+                // the last bit of the lanes before it (exclusive running max), else the carry
+                uint32_t enc = 0;                                          // (last position of my slice) + 1
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (w[q]) enc = tile_base + (lane * 8 + q) * 32 + (31 - __clz(w[q])) + 1;
+                uint32_t run = enc;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d) * (lane >= (uint32_t)d));
+                uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
+                if (lane == 0) pred = 0;
+                pred = max(pred, carry);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t v = w[q];
+                    const uint32_t wb = tile_base + (lane * 8 + q) * 32;
+                    while (v) {
+                        const uint32_t cur = wb + __ffs(v) - 1;
+                        v &= v - 1;
+                        if (pred) {
+                            const uint32_t gap = cur - (pred - 1);
+                            add_gap(acc, gap, hist, a.hist_bins);
+                            if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
+                        } else {
+                            first = cur + 1;
+                        }
+                        pred = cur + 1;
+                    }
+                }
+                carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
+            }
+            }                                                              // if (any)
+            b0 = b1; b1 = b2; b2 = b3;
+#pragma unroll
+            for (int l = 0; l < DT_MAXL; ++l) pv[l] = pn[l];
+        }
+        // ---- the set: gaps between the ranges of consecutive non-empty warps, then block reductions ----
+        first = __reduce_max_sync(0xffffffffu, first);                    // one lane set it
+        if (lane == 0) { s_first[warp] = first; s_last[warp] = carry; }
+        __syncthreads();
+        if (tid == 0) {
+            GapAcc x;
+            x.cnt = 0; x.maxgap = 0; x.sumsq = 0;
+            uint32_t prev = 0;
+            for (uint32_t wv = 0; wv < DT_WARPS; ++wv) {
+                if (!s_last[wv]) continue;
+                if (prev) {
+                    const uint32_t gap = s_first[wv] - prev;              // both carry the + 1
+                    add_gap(x, gap, hist, a.hist_bins);
+                    if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
+                }
+                prev = s_last[wv];
+            }
+            s_cross = x;
+        }
+        __syncthreads();
+        const uint32_t n = block_reduce_dt(acc.cnt, OpAddU32(), 0u, s_red32) + s_cross.cnt;          // number of gaps
+        const uint32_t mx = max(block_reduce_dt(acc.maxgap, OpMaxU32(), 0u, s_red32), s_cross.maxgap);
+        const unsigned long long ssq = block_reduce_dt(acc.sumsq, OpAddU64(), 0ull, s_red64) + s_cross.sumsq;
+        const uint32_t fst1 = block_reduce_dt(first ? first : 0xffffffffu, OpMinU32(), 0xffffffffu, s_red32);
+        const uint32_t lst1 = block_reduce_dt(carry, OpMaxU32(), 0u, s_red32);
+        const unsigned long long H = lst1 ? (unsigned long long)(lst1 - fst1) : 0ull;
+        const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
+        const bool hist_ok = mx < a.hist_bins;
+        // ---- rank-weighted sum from the histogram (and clear it) ----
+        unsigned long long sum_prefix = 0;
+        if (a.hist_bins) {
+            const uint32_t top = min(mx, a.hist_bins - 1);                    // highest bin that can be non-zero
+            const uint32_t per = top / DT_THREADS + 1;
+            const uint32_t b0 = tid * per, b1 = min(b0 + per, top + 1);
+            uint32_t c_mine = 0;
+            for (uint32_t v = b0; v < b1; ++v) c_mine += hist[v];
+            uint32_t inc = c_mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (uint32_t)d) inc += o;
+            }
+            __syncthreads();
+            if (lane == 31) s_scan[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t v = s_scan[lane];
+                uint32_t vi = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, vi, d);
+                    if (lane >= (uint32_t)d) vi += o;
+                }
+                s_scan[lane] = vi - v;
+            }
+            __syncthreads();
+            unsigned long long r = s_scan[warp] + inc - c_mine;               // gaps smaller than my first bin
+            unsigned long long part = 0;
+            for (uint32_t v = b0; v < b1; ++v) {
+                const unsigned long long c = hist[v];
+                hist[v] = 0;
+                if (c) {
+                    part += (unsigned long long)v * (c * ((unsigned long long)n - r) - c * (c - 1) / 2);
+                    r += c;
+                }
+            }
+            sum_prefix = block_reduce_dt(part, OpAddU64(), 0ull, s_red64);
+        }
+        if (tid == 0) {
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            double mean = nan, sd = nan, gini = nan, score = nan;
+            if (n > 0) {
+                mean = (double)H / (double)n;                                  // stats.py:12
+                if (n > 1) {
+                    const unsigned long long a_lo = (unsigned long long)n * ssq, a_hi = __umul64hi(n, ssq);
+                    const unsigned long long b_lo = H * H, b_hi = __umul64hi(H, H);
+                    const unsigned long long d_lo = a_lo - b_lo, d_hi = a_hi - b_hi - (a_lo < b_lo ? 1ull : 0ull);
+                    const double num = (double)d_hi * 18446744073709551616.0 + (double)d_lo;
+                    sd = sqrt(num / ((double)n * (double)(n - 1)));            // stats.py:17-19
+                }
+                if (a.hist_bins && hist_ok) {
+                    const unsigned long long fair = (H * (unsigned long long)n) / 2;   // Python-2 floor, stats.py:53
+                    if (fair > 0) {
+                        const long long two_area = (long long)(2 * sum_prefix) - (long long)H;
+                        gini = (double)((long long)(2 * fair) - two_area) / (double)(2 * fair);
+                    }
+                }
+                score = (mean * gini) / a.bg_dist_mean[s];
+            }
+            a.n_sites[s] = lst1 ? n + 1 : 0;
+            a.max_dist[s] = mx;
+            a.mean[s] = mean;
+            a.stdev[s] = sd;
+            a.gini[s] = gini;
+            a.score[s] = score;
+            a.status[s] = (uint8_t)((passed ? 1 : 0) | ((!hist_ok) ? 2 : 0));
+        }
+        __syncthreads();
     }
 }
 
@@ -488,6 +819,13 @@ k_score_sort(ScoreArgs a)
     }
 }
 
+__global__ void k_score_all_ids(uint32_t *__restrict__ ids, uint32_t *__restrict__ n, uint32_t S)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) ids[s] = s;
+    if (s == 0) *n = S;
+}
+
 // Splits the sets by raw site count: ids[0 .. n[0]) = sets for k_score_sort (raw <= cap), ids[S .. S + n[1]) = the rest.
 __global__ void __launch_bounds__(256)
 k_score_classify(ScoreArgs a, uint32_t *__restrict__ ids, uint32_t *__restrict__ n)
@@ -537,7 +875,7 @@ k_gini_sorted(const uint32_t *__restrict__ gaps, uint32_t n, double *__restrict_
 int swga_radix_sort_pairs(swga_ctx *ctx, uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b,
                           uint64_t n, int bits, bool vals_are_index, int *result_in_a, cudaStream_t stream);
 
-extern "C" uint32_t swga_score_tile_shift(void) { return SC_TILE_SHIFT; }
+extern "C" uint32_t swga_score_tile_shift(void) { return DT_SHIFT; }
 extern "C" uint32_t swga_score_max_hist_bins(void)
 {
     return (227u * 1024u - 4u * (SC_L0_PHYS + SC_L1_WORDS) - 2048u) / 4u;
@@ -582,12 +920,19 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         k_score_sort<<<grid_s, SS_THREADS, smem_s, as_stream(stream)>>>(a);
         CUDA_TRY(cudaGetLastError());
     }
-    const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS + a.hist_bins);
-    CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the rest: one warp per fine tile (k_score_dense)
+    const size_t smem = 4ull * DT_WARPS * DT_WORDS + 2ull * DT_WARPS * DT_LIST_CAP + 4ull * a.hist_bins;
+    CUDA_TRY(cudaFuncSetAttribute(k_score_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = S < (uint32_t)ctx->sm_count ? S : (uint32_t)ctx->sm_count;
-    a.ids = a.sort_cap ? ids + S : nullptr;
-    a.n_ids = n_ids + 1;
-    k_score<<<grid, SC_THREADS, smem, as_stream(stream)>>>(a);
+    if (a.sort_cap) {
+        a.ids = ids + S;
+        a.n_ids = n_ids + 1;
+    } else {                                                   // no sparse kernel: every set is "dense"
+        k_score_all_ids<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(ids + S, n_ids + 1, S);
+        a.ids = ids + S;
+        a.n_ids = n_ids + 1;
+    }
+    k_score_dense<<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
