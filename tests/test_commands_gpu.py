@@ -1,0 +1,101 @@
+"""`init -> count -> filter -> find_sets -> score` through swga_b200.commands on a workspace database,
+compared with the oracle restatement of the reference's commands (swga/commands/*.py)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ws_dir(tmp_path_factory):
+    from swga_b200 import synth
+    d = tmp_path_factory.mktemp("wsdb")
+    fg_seq = synth.bases(71, 0, 300_000, 0.32)
+    bg_seq = synth.bases(72, 0, 3_000_000, 0.44)
+    synth.write_fasta(str(d / "fg.fa"), fg_seq, np.array([0, 120_000, 300_000], dtype=np.uint64), ["chrA", "chrB"])
+    synth.write_fasta(str(d / "bg.fa"), bg_seq, np.array([0, 3_000_000], dtype=np.uint64))
+    return d
+
+
+def test_commands_end_to_end(ws_dir, oracle):
+    from swga_b200 import commands, workspace
+    db = str(ws_dir / "primers.db")
+    fg, bg = str(ws_dir / "fg.fa"), str(ws_dir / "bg.fa")
+    params = commands.init(fg, bg, db_name=db)
+    assert params["count"]["min_fg_bind"] == int(1e-5 * 300_000) and params["count"]["max_bg_bind"] == int(6.7e-6 * 3_000_000)
+    with pytest.raises(commands.CommandError):
+        commands.init(fg, bg, db_name=db)                                # existing workspace, no force
+
+    # ---- count: every row the reference's merge would insert (count.py:84-135), both strands
+    n = commands.count(db_name=db, min_size=6, max_size=8, min_fg_bind=15, max_bg_bind=200, max_dimer_bp=3)
+    fgd, bgd = open(fg, "rb").read(), open(bg, "rb").read()
+    want = {}
+    for k in range(6, 9):
+        f, b = oracle.count_kmers_dict(fgd, k), oracle.count_kmers_dict(bgd, k)
+        for seq in f:
+            p = oracle.primer_dict(seq, f, b, 15, 200, 3)
+            if p:
+                want[seq] = (p["fg_freq"], p["bg_freq"], p["ratio"])
+                want[oracle.revcomp(seq)] = want[seq]
+    with workspace.connection(db) as ws:
+        got = {p.seq: (p.fg_freq, p.bg_freq, p.ratio) for p in ws.primers()}
+    assert n == len(got) and got == want
+    with pytest.raises(commands.CommandError):
+        commands.count(db_name=db, min_size=6, max_size=6)               # would delete rows: needs force
+
+    # ---- filter: the active set, locations and Gini of the primers that reached that step
+    active = commands.filter(db_name=db, max_primers=30, min_fg_bind=15, max_bg_bind=200, max_gini=0.85)
+    assert 4 < len(active) <= 30
+    recs = oracle.fasta_records_pyfaidx(fgd)
+    ends = oracle.chromosome_ends(recs)
+    with workspace.connection(db) as ws:
+        act = ws.primers('"active" = 1')
+        assert sorted(p.seq for p in act) == sorted(active)
+        for p in act:
+            loc = oracle.binding_sites(p.seq, recs)
+            assert p.locations == loc
+            assert p.gini == oracle.gini(oracle.seq_diff(oracle.linearize_binding_sites([loc], ends)))
+    # the reference's chain on the same rows: fg >= , bg <=, the 30 least bg-binding, gini <= 0.85
+    rows = sorted(((s,) + v for s, v in want.items() if v[0] >= 15 and v[1] <= 200), key=lambda r: r[2])
+    assert len(active) <= len(rows)
+
+    # ---- find_sets: rows of `set` equal the oracle's replay of the same set_finder stream
+    graph = str(ws_dir / "g.dimacs")
+    found = commands.find_sets(db_name=db, min_size=2, max_size=3, max_dimer_bp=3, min_bg_bind_dist=2000,
+                               max_fg_bind_dist=20000, max_sets=12, graph_fp=graph)
+    assert 0 < len(found) <= 12
+    with workspace.connection(db) as ws:
+        by_id = {p._id: p for p in ws.primers('"active" = 1')}
+        sets_db = ws.sets()
+    assert sorted(by_id) == list(range(1, len(by_id) + 1))               # Primers.assign_ids
+    assert [r["_id"] for r in sets_db] == list(range(1, len(found) + 1))
+    from swga_b200 import sets
+    gen = sets.find(min_bg_bind_dist=2000, min_size=2, max_size=3, bg_length=3_000_000, graph_fp=graph)
+    passed = []
+    for line in gen:
+        ids, bgm = oracle.read_set_finder_line(line)
+        sc, var, md = oracle.score_set([by_id[i].locations for i in ids], 20000, bgm, ends)
+        if sc is not False:
+            passed.append((ids, sc, var, md))
+            if len(passed) >= 12:
+                break
+    gen.close()
+    assert len(passed) == len(sets_db)
+    for row, (ids, sc, var, md) in zip(sets_db, passed):
+        assert sorted(row["primers"]) == sorted(by_id[i].seq for i in ids)
+        assert row["fg_max_dist"] == md and row["set_size"] == len(ids)
+        assert row["fg_dist_mean"] == var["fg_dist_mean"] and row["fg_dist_gini"] == var["fg_dist_gini"]
+        assert row["score"] == pytest.approx(sc, rel=1e-12)
+    with pytest.raises(commands.CommandError):
+        commands.find_sets(db_name=db, graph_fp=graph)                   # sets exist: needs force
+
+    # ---- score: a user-defined set, never rejected, stored under a negative id
+    seqs = [by_id[1].seq, by_id[2].seq, by_id[3].seq]
+    out = commands.score_set(db_name=db, primers=seqs, force=True)
+    bgm = oracle.calculate_bg_dist_mean([by_id[i].bg_freq for i in (1, 2, 3)], 3_000_000)
+    sc, var, md = oracle.score_set([by_id[i].locations for i in (1, 2, 3)], 0, bgm, ends, interactive=True)
+    assert out["_id"] == -1 and out["fg_max_dist"] == md and out["score"] == pytest.approx(sc, rel=1e-12)
+    out2 = commands.score_set(db_name=db, primers=[by_id[4].seq, by_id[5].seq], force=True)
+    assert out2["_id"] == -2
