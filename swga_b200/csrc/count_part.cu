@@ -305,7 +305,10 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
             if (g * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
         }
         __syncthreads();
-        // ---- per warp: reserve the global range of the runs of its buckets (whole chunks of 8), re-arm ----
+        // ---- per warp: reserve the global range of the runs of its buckets, re-arm ----
+        // Only WHOLE chunks of 8 leave the staging area; the up to 7 elements left over stay at the head of the
+        // bucket's range for the next tile, so padding is written once per (CTA, bucket), with the last tile.
+        const bool last = tile + gridDim.x >= n_tiles;
         uint32_t A_[ROUNDS], at_[ROUNDS];                      // A = staged | first slot << 15 | does-not-fit << 31
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
@@ -315,13 +318,13 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
             const uint32_t b = unit * 32 + lane;
             const uint32_t f = fill[b], i0 = init[b];
             const uint32_t u = (int32_t)f < 0 ? 0x4000u - (i0 >> 17) : ((f - i0) & 0x1FFFFu) >> 1;   // elements staged
-            const uint32_t ru = (u + 7u) & ~7u;
+            const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;       // elements that leave now
             uint32_t at = 0, part = 0;
-            if (u) {
+            if (ru) {
                 at = atomicAdd(cursor + b, ru);
                 part = at + ru > __ldg(base + b + 1);          // beyond the end of the bucket in `data`
             }
-            fill[b] = i0;
+            fill[b] = i0 + (last ? 0u : (u & 7u) * PT_ADD);
             A_[r] = u | ((i0 & 0x1FFFFu) >> 1) << 15 | part << 31;
             at_[r] = at;
         }
@@ -356,7 +359,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 const int k = sr * 8 + (int)(lane >> 2);
                 const uint32_t A = __shfl_sync(0xffffffffu, A_[r], k);
                 const uint32_t at = __shfl_sync(0xffffffffu, at_[r], k);
-                const uint32_t u = A & 0x7FFFu;
+                const uint32_t u = last ? ((A & 0x7FFFu) + 7u) & ~7u : A & 0x7FF8u;   // whole chunks only
                 uint32_t cc = (lane & 3u) * 8u;                // first element of this lane's chunk
                 unsigned char *sp = stg + 2u * ((A >> 15) & 0xFFFFu) + 2u * cc;
                 uint16_t *gp = data + at + cc;
@@ -387,6 +390,17 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                             }
                         }
                     }
+                }
+            }
+            // the left-over chunk of each of my buckets moves to the head of its range
+            __syncwarp();
+            if (!last) {
+                const uint32_t u = A_[r] & 0x7FFFu, whole = u & ~7u;
+                if ((u & 7u) && whole) {
+                    unsigned char *sp = stg + 2u * ((A_[r] >> 15) & 0xFFFFu);
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sp + 2u * whole);
+                    *reinterpret_cast<uint4 *>(sp + 2u * whole) = padv;
+                    *reinterpret_cast<uint4 *>(sp) = v;
                 }
             }
         }
@@ -509,7 +523,7 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     // upper bound of the layout (sum of estimate + slack over the buckets; Cauchy-Schwarz on the sqrt terms)
     const double s_tot = (double)n_sampled * 32.0;
     const uint32_t n_tiles = (uint32_t)((n_starts + PT_TILE - 1) / PT_TILE);
-    const uint64_t pad = (uint64_t)n_tiles * (PT_CH / 2);      // expected padding per bucket: (PT_CH - 1) / 2 per tile
+    const uint64_t pad = 2ull * ctx->sm_count * PT_CH;         // padding per bucket: one partial chunk per CTA, with its last tile
     const uint64_t capacity = (uint64_t)((double)n_groups * 32.0 * (17.0 / 16.0) + 8.0 * ratio * sqrt((double)nb * (s_tot + nb)) +
                                          (1033.0 + (double)pad) * nb + 64.0 * ratio + 4096.0);
     if (capacity >= 0xFFFFFFF0ull) return SWGA_OK;            // offsets are 32-bit
