@@ -225,6 +225,22 @@ k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n
 }
 
 // ---- (3) scatter the low bits into prefix buckets --------------------------------------------------
+// The last, partial chunk of a run: element of rank r sits at position r ^ x of the chunk (x = bucket & 7, the
+// bank swizzle); positions whose rank is >= nv hold stale data and become padding.
+__device__ __forceinline__ uint4 pad_partial_chunk(uint4 v, uint32_t nv, uint32_t x, const uint4 &padv)
+{
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t pw[4] = {padv.x, padv.y, padv.z, padv.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (((uint32_t)q ^ x) >= nv) {
+            const uint32_t m = 0xFFFFu << (16 * (q & 1));
+            w[q >> 1] = (w[q >> 1] & ~m) | (pw[q >> 1] & m);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(PT_THREADS, 2)
 k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
@@ -247,9 +263,9 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     uint32_t *__restrict__ top = tables + offs.off[KMAX];
     if (tid < 4) s_stats[tid] = 0;
 
-    // The staging area always holds padding wherever no element of the current tile was staged: filled
-    // here, and every chunk copied out is replaced by padding.  Pad values are 0x4000 | r, r < 64: they
-    // land in k_bucket_count's dump bins, spread so that they do not pile up on one shared-memory word.
+    // Padding (only the last chunk a CTA writes into a bucket, and the chunks of the overflow list, carry any):
+    // values 0x4000 | r, r < 64, which land in k_bucket_count's dump bins, spread so that they do not pile up
+    // on one shared-memory word.
     uint4 padv;
     {
         const uint32_t r0 = lane * 8;
@@ -258,7 +274,6 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
         padv.z = PT_PAD_WORD | ((r0 + 4) & 63) | (((r0 + 5) & 63) << 16);
         padv.w = PT_PAD_WORD | ((r0 + 6) & 63) | (((r0 + 7) & 63) << 16);
     }
-    for (uint32_t i = tid; i < PT_STAGE / 8; i += PT_THREADS) reinterpret_cast<uint4 *>(stg)[i] = padv;
     for (uint32_t i = tid; i < NB; i += PT_THREADS) {
         const uint32_t v = init_g[i];
         init[i] = v;
@@ -349,7 +364,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 }
             }
         }
-        // ---- copy the runs: 4 lanes per bucket, one 16-byte chunk per lane and trip; leave padding behind ----
+        // ---- copy the runs: 4 lanes per bucket, one 16-byte chunk per lane and trip ----
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t b0 = (r * WARPS + warp) * 32;
@@ -359,23 +374,24 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 const int k = sr * 8 + (int)(lane >> 2);
                 const uint32_t A = __shfl_sync(0xffffffffu, A_[r], k);
                 const uint32_t at = __shfl_sync(0xffffffffu, at_[r], k);
-                const uint32_t u = last ? ((A & 0x7FFFu) + 7u) & ~7u : A & 0x7FF8u;   // whole chunks only
+                const uint32_t staged = A & 0x7FFFu;
+                const uint32_t u = last ? (staged + 7u) & ~7u : staged & ~7u;          // whole chunks only
                 uint32_t cc = (lane & 3u) * 8u;                // first element of this lane's chunk
                 unsigned char *sp = stg + 2u * ((A >> 15) & 0xFFFFu) + 2u * cc;
                 uint16_t *gp = data + at + cc;
                 if ((int32_t)A >= 0) {
 #pragma unroll 1
                     for (; cc < u; cc += 32u, sp += 64, gp += 32) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(sp);
-                        *reinterpret_cast<uint4 *>(sp) = padv;
+                        uint4 v = *reinterpret_cast<const uint4 *>(sp);
+                        if (staged - cc < 8u) v = pad_partial_chunk(v, staged - cc, (b0 + k) & 7u, padv);   // last tile only
                         *reinterpret_cast<uint4 *>(gp) = v;
                     }
                 } else {                                       // the run crosses the end of its bucket
                     const uint32_t l = __ldg(base + b0 + k + 1);
 #pragma unroll 1
                     for (; cc < u; cc += 32u, sp += 64, gp += 32) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(sp);
-                        *reinterpret_cast<uint4 *>(sp) = padv;
+                        uint4 v = *reinterpret_cast<const uint4 *>(sp);
+                        if (staged - cc < 8u) v = pad_partial_chunk(v, staged - cc, (b0 + k) & 7u, padv);
                         if (at + cc + 8u <= l) {
                             *reinterpret_cast<uint4 *>(gp) = v;
                         } else {                               // straight to the table
@@ -398,9 +414,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 const uint32_t u = A_[r] & 0x7FFFu, whole = u & ~7u;
                 if ((u & 7u) && whole) {
                     unsigned char *sp = stg + 2u * ((A_[r] >> 15) & 0xFFFFu);
-                    const uint4 v = *reinterpret_cast<const uint4 *>(sp + 2u * whole);
-                    *reinterpret_cast<uint4 *>(sp + 2u * whole) = padv;
-                    *reinterpret_cast<uint4 *>(sp) = v;
+                    *reinterpret_cast<uint4 *>(sp) = *reinterpret_cast<const uint4 *>(sp + 2u * whole);
                 }
             }
         }
