@@ -215,7 +215,9 @@ int swga_tile_offsets(swga_ctx *ctx, const uint32_t *d_sites, const uint64_t *d_
  *   d_sites / d_toff  site lists (sorted, unique, linearised) of every primer plus one extra list,
  *                     id `bounds_list`, holding the first and last position of every record
  *                     (locate.py:30-32 adds them for every primer); tile offsets from
- *                     swga_tile_offsets with tile_shift = swga_score_tile_shift()
+ *                     swga_tile_offsets with tile_shift = swga_score_tile_shift().  d_sites must be
+ *                     16-byte aligned and readable for 16 words past the last site (the dense kernel
+ *                     fetches the lists with aligned 16-byte loads)
  *   d_sets            [S][max_m] list ids, -1 padded
  *   d_bg_dist_mean    [S] (set_finder's weight or score.calculate_bg_dist_mean)
  * Outputs per set: n_sites (unique positions), max_dist, mean / stdev / gini of the gaps, the default

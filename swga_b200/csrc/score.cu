@@ -310,7 +310,6 @@ k_score(ScoreArgs a)
 #define DT_WARPS (DT_THREADS / 32)
 #define DT_WORDS ((1u << DT_SHIFT) / 32)                   // 256 bitmap words per warp
 #define DT_LIST_CAP 512u                                   // compact list entries per warp (uint16)
-#define DT_MAXL 12                                         // lists whose first 32 sites per tile are prefetched
 
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce_dt(T v, Op op, T ident, T *scratch /* DT_WARPS + 1 */)
@@ -335,6 +334,26 @@ __device__ __forceinline__ uint32_t ld_pinned(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint4 ld_pinned4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// 16-bit shared-memory accesses through a 32-bit shared address computed once (the generic-pointer form makes
+// the compiler rebuild the shared window base inside every unrolled loop body)
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
 
@@ -366,7 +385,7 @@ k_score_dense(ScoreArgs a)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *bm = bm_all + warp * DT_WORDS;
-    uint16_t *cl = cl_all + warp * DT_LIST_CAP;
+    const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + warp * DT_LIST_CAP);
     for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
@@ -388,56 +407,78 @@ k_score_dense(ScoreArgs a)
         }
         __syncthreads();
         const uint32_t nl = s_nlists;
-        const uint32_t *row = a.toff + (uint64_t)s_list[lane < nl ? lane : 0] * (a.n_tiles + 1);
 
         GapAcc acc;
         acc.cnt = 0; acc.maxgap = 0; acc.sumsq = 0;
         uint32_t carry = 0, first = 0;                                     // (position + 1); 0 = none yet
         const uint32_t t0 = min(a.n_tiles, warp * tpw), t1 = min(a.n_tiles, t0 + tpw);
-        // Software pipeline over the warp's tiles: the segment bounds are read two tiles ahead and the first 32
-        // sites of every list of tile t + 1 are loaded while tile t is processed (one L2 latency per tile
-        // instead of one per list).
+        // Software pipeline over the warp's tiles.  Lane = (list lane & 15, half lane >> 4): it reads two aligned
+        // 16-byte chunks of its list's segment of a tile (half 0: the chunks at aligned element offsets 0 and 4,
+        // half 1: 8 and 12), i.e. the first 13..16 sites of each of up to 16 lists in ONE load instruction per
+        // lane pair, one tile ahead (the loads of tile t + 1 fly while tile t is processed); the segment bounds
+        // are read two tiles ahead.  Longer segments and lists beyond 16 take the scalar loop below.
+        const uint32_t mylist = lane & 15u, half = lane >> 4;
+        const uint32_t *row = a.toff + (uint64_t)s_list[mylist < nl ? mylist : 0] * (a.n_tiles + 1);
         uint32_t b0 = 0, b1 = 0, b2 = 0;                                   // row[t], row[t + 1], row[t + 2] of my list
-        if (lane < nl && t0 < t1) {
+        if (mylist < nl && t0 < t1) {
             b0 = row[t0];
             b1 = row[min(a.n_tiles, t0 + 1)];
             b2 = row[min(a.n_tiles, t0 + 2)];
         }
-        uint32_t pv[DT_MAXL];                                              // sites of the current tile, list l, index `lane`
-#pragma unroll
-        for (int l = 0; l < DT_MAXL; ++l) {
-            const uint32_t lo_l = __shfl_sync(0xffffffffu, b0, l), len_l = __shfl_sync(0xffffffffu, b1 - b0, l);
-            pv[l] = lane < len_l ? ld_pinned(a.sites + lo_l + lane) : 0xffffffffu;
+        uint4 pa = make_uint4(0, 0, 0, 0), pb = pa;                        // chunks of the current tile
+        if (b1 > b0) {
+            const uint4 *c = reinterpret_cast<const uint4 *>(a.sites + (b0 & ~3u)) + 2 * half;
+            pa = ld_pinned4(c);
+            pb = ld_pinned4(c + 1);
         }
         for (uint32_t t = t0; t < t1; ++t) {
             const uint32_t lo = b0, len = b1 - b0;
             // next tile: bounds are here already; its sites and the bounds after it start their trip now
-            uint32_t pn[DT_MAXL];
-#pragma unroll
-            for (int l = 0; l < DT_MAXL; ++l) {
-                const uint32_t lo_l = __shfl_sync(0xffffffffu, b1, l), len_l = __shfl_sync(0xffffffffu, b2 - b1, l);
-                pn[l] = (t + 1 < t1 && lane < len_l) ? ld_pinned(a.sites + lo_l + lane) : 0xffffffffu;
+            uint4 na = make_uint4(0, 0, 0, 0), nb4 = na;
+            if (t + 1 < t1 && b2 > b1) {
+                const uint4 *c = reinterpret_cast<const uint4 *>(a.sites + (b1 & ~3u)) + 2 * half;
+                na = ld_pinned4(c);
+                nb4 = ld_pinned4(c + 1);
             }
-            const uint32_t b3 = (lane < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
+            const uint32_t b3 = (mylist < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
             const uint32_t tile_base = t << DT_SHIFT;
-            const uint32_t any = __reduce_add_sync(0xffffffffu, len);
-            const uint32_t longest = __reduce_max_sync(0xffffffffu, len);
+            const uint32_t covered = 16u - (lo & 3u);                      // sites of my list the chunks hold
+            bool any = __any_sync(0xffffffffu, len != 0);
+            uint32_t need = __ballot_sync(0xffffffffu, len > covered) & 0xFFFFu;   // lists with sites beyond the chunks
+            if (nl > 16) {                                                 // lists no lane owns
+                for (uint32_t l = 16; l < nl && !any; ++l) {
+                    const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
+                    any = r[1] > r[0];
+                }
+            }
             if (any) {
             // ---- (2) one bit per site ----
+            {
+                const uint32_t v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                const uint32_t first_idx = 8u * half - (lo & 3u);          // index in the segment of v[0] (may wrap below 0)
 #pragma unroll
-            for (int l = 0; l < DT_MAXL; ++l) {
-                if (pv[l] != 0xffffffffu) {
-                    const uint32_t p = pv[l] - tile_base;
+                for (int q = 0; q < 8; ++q) {
+                    if (first_idx + q < len) {                             // unsigned: also false before the segment
+                        const uint32_t p = v[q] - tile_base;
+                        atomicOr(&bm[p >> 5], 1u << (p & 31));
+                    }
+                }
+            }
+            while (need) {                                                 // what the chunks do not cover
+                const int l = __ffs(need) - 1;
+                need &= need - 1;
+                const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
+                for (uint32_t i = 16u - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                    const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
                     atomicOr(&bm[p >> 5], 1u << (p & 31));
                 }
             }
-            if (longest > 32 || nl > DT_MAXL) {                            // what the prefetch does not cover
-                for (uint32_t l = 0; l < nl; ++l) {
-                    const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
-                    for (uint32_t i = (l < DT_MAXL ? 32u : 0u) + lane; i < len_l; i += 32) {
-                        const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
-                        atomicOr(&bm[p >> 5], 1u << (p & 31));
-                    }
+            for (uint32_t l = 16; l < nl; ++l) {
+                const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
+                const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
+                for (uint32_t i = lane; i < len_l; i += 32) {
+                    const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
+                    atomicOr(&bm[p >> 5], 1u << (p & 31));
                 }
             }
             __syncwarp();
@@ -461,30 +502,30 @@ k_score_dense(ScoreArgs a)
             }
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total <= DT_LIST_CAP) {
-                uint32_t idx = incl - c;
+                uint32_t ad = cl_s + 2u * (incl - c);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t v = w[q];
-                    const uint32_t wb = (lane * 8 + q) * 32;
+                    const uint32_t wb = (lane * 8 + q) * 32 - 1;
                     while (v) {
-                        cl[idx++] = (uint16_t)(wb + __ffs(v) - 1);
+                        sts_u16(ad, wb + __ffs(v));
+                        ad += 2;
                         v &= v - 1;
                     }
                 }
                 __syncwarp();
                 // ---- (4) gaps, all lanes busy ----
                 for (uint32_t j = lane; j < total; j += 32) {
-                    const uint32_t cur = tile_base + cl[j];
-                    const uint32_t prev1 = j ? tile_base + cl[j - 1] + 1 : carry;
+                    const uint32_t cur = tile_base + lds_u16(cl_s + 2u * j);
+                    const uint32_t prev1 = j ? tile_base + lds_u16(cl_s + 2u * j - 2u) + 1 : carry;
                     if (prev1) {
                         const uint32_t gap = cur - (prev1 - 1);
                         add_gap(acc, gap, hist, a.hist_bins);
-                        if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
                     } else {
                         first = cur + 1;
                     }
                 }
-                carry = tile_base + cl[total - 1] + 1;
+                carry = tile_base + lds_u16(cl_s + 2u * total - 2u) + 1;
                 __syncwarp();
             } else {
                 // more distinct sites than the list holds: each lane walks its own bits; its predecessor is
@@ -509,8 +550,7 @@ k_score_dense(ScoreArgs a)
                         if (pred) {
                             const uint32_t gap = cur - (pred - 1);
                             add_gap(acc, gap, hist, a.hist_bins);
-                            if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
-                        } else {
+                            } else {
                             first = cur + 1;
                         }
                         pred = cur + 1;
@@ -520,8 +560,7 @@ k_score_dense(ScoreArgs a)
             }
             }                                                              // if (any)
             b0 = b1; b1 = b2; b2 = b3;
-#pragma unroll
-            for (int l = 0; l < DT_MAXL; ++l) pv[l] = pn[l];
+            pa = na; pb = nb4;
         }
         // ---- the set: gaps between the ranges of consecutive non-empty warps, then block reductions ----
         first = __reduce_max_sync(0xffffffffu, first);                    // one lane set it
@@ -536,7 +575,6 @@ k_score_dense(ScoreArgs a)
                 if (prev) {
                     const uint32_t gap = s_first[wv] - prev;              // both carry the + 1
                     add_gap(x, gap, hist, a.hist_bins);
-                    if (a.gap_out) a.gap_out[atomicAdd(a.gap_count, 1u)] = gap;
                 }
                 prev = s_last[wv];
             }

@@ -90,6 +90,9 @@ class SiteLists(object):
         self.dev = torch.device("cuda", self.ctx.device)
         self.sites = sites if is_t else torch.from_numpy(
             np.ascontiguousarray(sites, dtype=np.uint32).view(np.int32)).to(self.dev)
+        # swga_score_sets reads the lists with 16-byte vector loads: 16 readable words past the last site
+        self.n_sites_total = int(self.sites.numel())
+        self.sites = torch.cat([self.sites, torch.zeros(16, dtype=torch.int32, device=self.dev)])
         self.site_off = np.ascontiguousarray(site_off, dtype=np.uint64)
         self.n_lists = len(self.site_off) - 1
         self.n_primers = n_primers
