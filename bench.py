@@ -401,8 +401,8 @@ def run_b200_arm(args):
                                 "bytes_alg": stage_bytes, "achieved": stage_bytes / (count_ms * 1e-3) / 1e9,
                                 "frac": stage_bytes / (count_ms * 1e-3) / 1e9 / hbm_peak,
                                 "traffic": tr.get("dram_bytes_per_base", 0) * bg.n_starts or None},
-                "note": "k_partition is bound by the L1/shared-memory data pipe (ncu: l1tex data-pipe wavefronts 75 % of peak, "
-                        "DRAM 22 %), not by HBM: every element costs one shared atomic and one 2-byte shared store with "
+                "note": "k_partition is bound by the L1/shared-memory data pipe (ncu: l1tex data-pipe wavefronts 77-85 % of peak, "
+                        "DRAM 21 %), not by HBM: every element costs one shared atomic and one 2-byte shared store with "
                         "~3.8-way bank serialisation; see 'atomic' and profiles/r01_summary.md"}
     path_bytes = 1.5 * (fg.n + bg.n) + 2 * 2 * 4.0 * words       # 1.5 B/base + 2T per genome
     path = {"bytes_alg": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s"}
@@ -472,7 +472,7 @@ def run_b200_arm(args):
 
     # ---- size-independent parity properties of the full-size tables (no CPU oracle at 3.1 Gbp) ----
     props = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         step()
         torch.cuda.synchronize()
         ok = True
