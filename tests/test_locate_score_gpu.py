@@ -227,3 +227,59 @@ def test_set_index_sharding_needs_no_collective(quirky, oracle):
         for key in ("fg_max_dist", "n_sites", "fg_dist_mean", "fg_dist_gini", "score"):
             cat = np.concatenate([p[key] for p in parts])
             assert np.array_equal(cat, whole[key], equal_nan=True), (world, key)
+
+
+def test_scoring_kernels_edge_shapes(oracle):
+    """Constructed site lists that drive every branch of the two scoring kernels: merge-sort sizes around the
+    16-element segments and the capacity, duplicate positions across lists, sets of up to 31 lists (lists no
+    lane of the dense kernel owns), tile segments longer than the 16-byte chunk prefetch covers, and tiles with
+    more distinct sites than the compaction list holds (per-lane walk)."""
+    from swga_b200 import _lib, score
+    rng = np.random.RandomState(11)
+    L = 3_000_000
+    bounds = [0, 999_999, 1_000_000, L - 1]
+    lists = []
+    for n in (1, 2, 14, 15, 16, 17, 31, 33, 255, 256, 257, 1000, 2047, 4060):      # sparse, odd sizes
+        lists.append(np.sort(rng.choice(L, n, replace=False)))
+    lists.append(np.arange(500_000, 540_000, 3))                                   # 2,730 sites per 8,192-position tile
+    lists.append(np.arange(500_001, 600_000, 7))
+    lists.append(np.arange(2_000_000, 2_001_000))                                  # every position of a stretch
+    for n in (9000, 20000, 50000):                                                 # ordinary dense lists
+        lists.append(np.sort(rng.choice(L, n, replace=False)))
+    lists.append(lists[-1][::2].copy())                                            # shares every position with another list
+    while len(lists) < 34:
+        lists.append(np.sort(rng.choice(L, int(rng.randint(3000, 9000)), replace=False)))
+    sl = score.SiteLists.from_host_lists(lists, bounds, L)
+    P_ = len(lists)
+    max_m = 31
+    sets = []
+    for i in range(14):
+        sets.append([i])                                                           # one sparse list + bounds
+    sets += [[0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10, 11, 12, 13], [13], [11, 13], [14], [15], [14, 15, 16], [16],
+             [17, 18, 19, 20], [19, 20], list(range(14, 34)), list(range(3, 34)), list(range(0, 31)),
+             [21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 17, 18, 19, 14]]
+    for _ in range(25):
+        m = int(rng.randint(1, max_m + 1))
+        sets.append(list(rng.choice(P_, m, replace=False)))
+    arr = np.full((len(sets), max_m), -1, dtype=np.int32)
+    for i, s in enumerate(sets):
+        arr[i, :len(s)] = s
+    bgs = rng.uniform(10, 1e4, len(sets))
+    lib, ctx = _lib.load(), _lib.context(0)
+    try:
+        for cap in (4096, 0, 64, 16384):
+            _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, cap))
+            for max_fg in (36000, 2 ** 31 - 1):
+                res = score.score_sets(sl, arr, bgs, max_fg)
+                for i, s in enumerate(sets):
+                    pos = sorted(set(int(x) for l in s for x in lists[l]) | set(bounds))
+                    gaps = oracle.seq_diff(list(pos))
+                    mx = max(gaps)
+                    assert int(res.n_sites[i]) == len(pos) and int(res.fg_max_dist[i]) == mx, (cap, i)
+                    assert bool(res.passed[i]) == (mx <= max_fg)
+                    assert float(res.fg_dist_mean[i]) == oracle.mean(gaps)
+                    assert float(res.fg_dist_std[i]) == pytest.approx(oracle.stdev(gaps), rel=1e-12)
+                    if res.passed[i]:
+                        assert float(res.fg_dist_gini[i]) == oracle.gini(gaps), (cap, i)
+    finally:
+        _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
