@@ -671,6 +671,7 @@ k_score_dense(ScoreArgs a)
 #define SS_WARPS (SS_THREADS / 32)
 
 #define MS_E 16u                                        // elements per thread-level segment of the merge sort
+#define SS_RUN_PAD (MS_E * SC_MAX_LISTS)                // room for every list's tail up to a multiple of MS_E
 #define MS_PHYS(i) ((i) + ((i) >> 4))                   // one pad word per segment: lane-strided segment accesses hit 32 banks
 
 // ascending sorting network (bitonic) on 16 registers
@@ -745,6 +746,51 @@ __device__ __forceinline__ uint32_t *block_merge_sort(uint32_t *a, uint32_t *b, 
     return a;
 }
 
+// Merge of nr ALREADY SORTED runs a[rb[r] .. rb[r + 1]) (boundaries multiples of MS_E, run tails filled with
+// 0xffffffff) into one: ceil(log2(nr)) merge-path passes over pairs of neighbouring runs, no base sort.  The
+// primers' site lists arrive sorted, so this replaces the first sort of a set (8 passes + the register
+// network for ~2,000 sites) by 4 passes for 9-11 lists.  rb lives in shared memory and is overwritten.
+__device__ __forceinline__ uint32_t *block_merge_runs(uint32_t *a, uint32_t *b, uint32_t *rb, uint32_t nr)
+{
+    while (nr > 1) {
+        const uint32_t np = rb[nr], R = np / MS_E;
+        for (uint32_t seg = threadIdx.x; seg < R; seg += SS_THREADS) {
+            const uint32_t o = seg * MS_E;
+            uint32_t p = 0;
+            while (rb[min(2 * p + 2, nr)] <= o) ++p;               // pair of runs that holds output o
+            const uint32_t pair = rb[2 * p], pb = rb[min(2 * p + 1, nr)];
+            const uint32_t la = pb - pair, lb = rb[min(2 * p + 2, nr)] - pb, d = o - pair;
+            uint32_t lo = d > lb ? d - lb : 0u, hi = min(d, la);
+            while (lo < hi) {                                  // first i with A[i] > B[d - 1 - i]
+                const uint32_t mid = (lo + hi) >> 1;
+                if (a[MS_PHYS(pair + mid)] <= a[MS_PHYS(pb + d - 1 - mid)]) lo = mid + 1; else hi = mid;
+            }
+            uint32_t i = lo, j = d - lo;
+            uint32_t av = i < la ? a[MS_PHYS(pair + i)] : 0xffffffffu, bv = j < lb ? a[MS_PHYS(pb + j)] : 0xffffffffu;
+            uint32_t out[MS_E];
+#pragma unroll
+            for (int e = 0; e < (int)MS_E; ++e) {
+                const bool ta = j >= lb || (i < la && av <= bv);
+                out[e] = ta ? av : bv;
+                if (ta) { ++i; av = i < la ? a[MS_PHYS(pair + i)] : 0xffffffffu; }
+                else { ++j; bv = j < lb ? a[MS_PHYS(pb + j)] : 0xffffffffu; }
+            }
+#pragma unroll
+            for (int e = 0; e < (int)MS_E; ++e) b[seg * (MS_E + 1) + e] = out[e];
+        }
+        __syncthreads();
+        const uint32_t nr2 = (nr + 1) / 2;
+        if (threadIdx.x == 0) {
+            for (uint32_t q = 0; q < nr2; ++q) rb[q] = rb[2 * q];
+            rb[nr2] = np;
+        }
+        nr = nr2;
+        __syncthreads();
+        uint32_t *t = a; a = b; b = t;
+    }
+    return a;
+}
+
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce_ss(T v, Op op, T ident, T *scratch /* SS_WARPS + 1 */)
 {
@@ -764,8 +810,8 @@ k_score_sort(ScoreArgs a)
 {
     extern __shared__ uint32_t smem[];
     uint32_t *buf = smem;                       // [cap2] positions
-    uint32_t *gaps = smem + MS_PHYS(a.sort_cap);  // [cap] gaps; both buffers in the padded layout MS_PHYS
-    __shared__ uint32_t s_src[SC_MAX_LISTS], s_len[SC_MAX_LISTS], s_dst[SC_MAX_LISTS];
+    uint32_t *gaps = smem + MS_PHYS(a.sort_cap + SS_RUN_PAD);  // second buffer; both in the padded layout MS_PHYS
+    __shared__ uint32_t s_src[SC_MAX_LISTS], s_len[SC_MAX_LISTS], s_rb[SC_MAX_LISTS + 1];   // s_rb: run starts, multiples of 16
     __shared__ uint32_t s_nl, s_raw, s_set;
     __shared__ uint32_t r32[SS_WARPS + 1];
     __shared__ unsigned long long r64[SS_WARPS + 1];
@@ -776,26 +822,27 @@ k_score_sort(ScoreArgs a)
         if (s_set >= *a.n_ids) break;
         const uint32_t s = a.ids[s_set];
         if (tid == 0) {
-            uint32_t n = 0, raw = 0;
+            uint32_t n = 0, raw = 0, at = 0;
             for (uint32_t j = 0; j <= a.max_m && n < SC_MAX_LISTS; ++j) {
                 int32_t id = j < a.max_m ? a.sets[(uint64_t)s * a.max_m + j] : (int32_t)a.bounds_list;
                 if (id < 0) continue;
                 const uint32_t *row = a.toff + (uint64_t)id * (a.n_tiles + 1);
                 const uint32_t lo = row[0], len = row[a.n_tiles] - lo;
-                s_src[n] = lo; s_len[n] = len; s_dst[n] = raw;
-                raw += len; ++n;
+                s_src[n] = lo; s_len[n] = len; s_rb[n] = at;
+                raw += len; at += (len + MS_E - 1) & ~(MS_E - 1); ++n;
             }
+            s_rb[n] = at;
             s_nl = n; s_raw = raw;
         }
         __syncthreads();
         const uint32_t raw = s_raw, nl = s_nl;
-        for (uint32_t l = 0; l < nl; ++l) {
-            const uint32_t len = s_len[l];
+        for (uint32_t l = 0; l < nl; ++l) {                                // every list is one sorted run, tail = 0xffffffff
+            const uint32_t len = s_len[l], at = s_rb[l], end = s_rb[l + 1];
             const uint32_t *src = a.sites + s_src[l];
-            for (uint32_t i = tid; i < len; i += SS_THREADS) buf[MS_PHYS(s_dst[l] + i)] = src[i];
+            for (uint32_t i = tid; i < end - at; i += SS_THREADS) buf[MS_PHYS(at + i)] = i < len ? src[i] : 0xffffffffu;
         }
         __syncthreads();
-        uint32_t *pos = block_merge_sort(buf, gaps, raw);              // sorted positions (duplicates kept)
+        uint32_t *pos = block_merge_runs(buf, gaps, s_rb, nl);         // sorted positions (duplicates kept)
         uint32_t *gp = pos == buf ? gaps : buf;
         // gaps between distinct neighbours; duplicates become the sentinel, which sorts last
         uint32_t cnt = 0, maxgap = 0;
@@ -951,7 +998,7 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         k_score_classify<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(a, ids, n_ids);
         CUDA_TRY(cudaGetLastError());
         a.ids = ids; a.n_ids = n_ids;
-        const size_t smem_s = 8ull * MS_PHYS(a.sort_cap);
+        const size_t smem_s = 8ull * MS_PHYS(a.sort_cap + SS_RUN_PAD);
         CUDA_TRY(cudaFuncSetAttribute(k_score_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem_s + 1024)));
         const uint32_t grid_s = std::min<uint32_t>(S, (uint32_t)ctx->sm_count * per_sm);
