@@ -672,6 +672,8 @@ k_score_dense(ScoreArgs a)
 
 #define MS_E 16u                                        // elements per thread-level segment of the merge sort
 #define SS_RUN_PAD (MS_E * SC_MAX_LISTS)                // room for every list's tail up to a multiple of MS_E
+#define SS_BINS 512u                                    // coarse bins of the gap grouping (Gini)
+#define SS_BIN_CROWD 256u                               // a bin with more gaps than this: use the merge sort
 #define MS_PHYS(i) ((i) + ((i) >> 4))                   // one pad word per segment: lane-strided segment accesses hit 32 banks
 
 // ascending sorting network (bitonic) on 16 registers
@@ -865,11 +867,72 @@ k_score_sort(ScoreArgs a)
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         unsigned long long sum_prefix = 0;
         if (passed && n > 0) {
+            // Gini's rank-weighted sum  sum_i g_(i) (n - i)  over the ascending gaps.  A counting sort by a coarse key
+            // (gap >> shift, SS_BINS bins, in the buffer the positions no longer need) groups the gaps; inside a
+            // bin (a handful of gaps) the rank is found by comparing with the bin's other members.  Exact for any
+            // input; a bin too crowded for that (or a set too large for the buffer) takes the full merge sort.
             __syncthreads();
-            const uint32_t *sg = block_merge_sort(gp, pos, raw);       // ascending gaps: Gini's rank-weighted sum
-            unsigned long long part = 0;
-            for (uint32_t i = tid; i < n; i += SS_THREADS) part += (unsigned long long)sg[MS_PHYS(i)] * (n - i);
-            sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
+            uint32_t *cnt = pos, *grouped = pos + SS_BINS;            // [SS_BINS] counts -> bin ends; [n] gaps by bin
+            const uint32_t room = MS_PHYS(a.sort_cap + SS_RUN_PAD) - SS_BINS;
+            uint32_t shift = 0;
+            while ((mx >> shift) >= SS_BINS) ++shift;
+            for (uint32_t i = tid; i < SS_BINS; i += SS_THREADS) cnt[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < raw; i += SS_THREADS) {
+                const uint32_t g = gp[MS_PHYS(i)];
+                if (g != 0xffffffffu) atomicAdd(&cnt[g >> shift], 1u);
+            }
+            __syncthreads();
+            // exclusive scan of the SS_BINS counts (SS_BINS / SS_THREADS consecutive bins per thread) + the fullest bin
+            uint32_t mine[SS_BINS / SS_THREADS], local = 0, fullest = 0;
+#pragma unroll
+            for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
+                mine[q] = cnt[tid * (SS_BINS / SS_THREADS) + q];
+                local += mine[q];
+                fullest = max(fullest, mine[q]);
+            }
+            uint32_t inc = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((tid & 31) >= (uint32_t)d) inc += o;
+            }
+            if ((tid & 31) == 31) r32[tid >> 5] = inc;
+            __syncthreads();
+            uint32_t before = inc - local;
+            for (uint32_t wq = 0; wq < (tid >> 5); ++wq) before += r32[wq];
+            __syncthreads();
+            fullest = block_reduce_ss(fullest, OpMaxU32(), 0u, r32);
+            if (fullest <= SS_BIN_CROWD && n <= room) {
+#pragma unroll
+                for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
+                    cnt[tid * (SS_BINS / SS_THREADS) + q] = before;      // start of the bin; the scatter turns it into its end
+                    before += mine[q];
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < raw; i += SS_THREADS) {
+                    const uint32_t g = gp[MS_PHYS(i)];
+                    if (g != 0xffffffffu) grouped[atomicAdd(&cnt[g >> shift], 1u)] = g;
+                }
+                __syncthreads();
+                unsigned long long part = 0;
+                for (uint32_t j = tid; j < n; j += SS_THREADS) {
+                    const uint32_t g = grouped[j], b = g >> shift;
+                    const uint32_t beg = b ? cnt[b - 1] : 0u, end = cnt[b];
+                    uint32_t rank = beg;                                 // gaps that sort before this one
+                    for (uint32_t k = beg; k < end; ++k) {
+                        const uint32_t o = grouped[k];
+                        rank += (o < g || (o == g && k < j)) ? 1u : 0u;
+                    }
+                    part += (unsigned long long)g * (n - rank);
+                }
+                sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
+            } else {
+                const uint32_t *sg = block_merge_sort(gp, pos, raw);   // ascending gaps
+                unsigned long long part = 0;
+                for (uint32_t i = tid; i < n; i += SS_THREADS) part += (unsigned long long)sg[MS_PHYS(i)] * (n - i);
+                sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
+            }
         }
         if (tid == 0) {
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
