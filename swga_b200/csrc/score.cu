@@ -672,7 +672,7 @@ k_score_dense(ScoreArgs a)
 
 #define MS_E 16u                                        // elements per thread-level segment of the merge sort
 #define SS_RUN_PAD (MS_E * SC_MAX_LISTS)                // room for every list's tail up to a multiple of MS_E
-#define SS_BINS 512u                                    // coarse bins of the gap grouping (Gini)
+#define SS_BINS 1024u                                   // coarse bins of the gap grouping (Gini)
 #define SS_BIN_CROWD 256u                               // a bin with more gaps than this: use the merge sort
 #define MS_PHYS(i) ((i) + ((i) >> 4))                   // one pad word per segment: lane-strided segment accesses hit 32 banks
 
