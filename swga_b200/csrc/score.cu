@@ -873,37 +873,42 @@ k_score_sort(ScoreArgs a)
             // input; a bin too crowded for that (or a set too large for the buffer) takes the full merge sort.
             __syncthreads();
             uint32_t *cnt = pos, *grouped = pos + SS_BINS;            // [SS_BINS] counts -> bin ends; [n] gaps by bin
-            const uint32_t room = MS_PHYS(a.sort_cap + SS_RUN_PAD) - SS_BINS;
-            uint32_t shift = 0;
-            while ((mx >> shift) >= SS_BINS) ++shift;
-            for (uint32_t i = tid; i < SS_BINS; i += SS_THREADS) cnt[i] = 0;
-            __syncthreads();
-            for (uint32_t i = tid; i < raw; i += SS_THREADS) {
-                const uint32_t g = gp[MS_PHYS(i)];
-                if (g != 0xffffffffu) atomicAdd(&cnt[g >> shift], 1u);
-            }
-            __syncthreads();
-            // exclusive scan of the SS_BINS counts (SS_BINS / SS_THREADS consecutive bins per thread) + the fullest bin
-            uint32_t mine[SS_BINS / SS_THREADS], local = 0, fullest = 0;
+            const uint32_t words = MS_PHYS(a.sort_cap + SS_RUN_PAD);  // of one buffer
+            const bool fits = words >= SS_BINS + n;                   // uniform
+            uint32_t shift = 0, fullest = 0xffffffffu, before = 0;
+            uint32_t mine[SS_BINS / SS_THREADS];
+            if (fits) {
+                while ((mx >> shift) >= SS_BINS) ++shift;
+                for (uint32_t i = tid; i < SS_BINS; i += SS_THREADS) cnt[i] = 0;
+                __syncthreads();
+                for (uint32_t i = tid; i < raw; i += SS_THREADS) {
+                    const uint32_t g = gp[MS_PHYS(i)];
+                    if (g != 0xffffffffu) atomicAdd(&cnt[g >> shift], 1u);
+                }
+                __syncthreads();
+                // exclusive scan of the counts (SS_BINS / SS_THREADS consecutive bins per thread) + the fullest bin
+                uint32_t local = 0;
+                fullest = 0;
 #pragma unroll
-            for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
-                mine[q] = cnt[tid * (SS_BINS / SS_THREADS) + q];
-                local += mine[q];
-                fullest = max(fullest, mine[q]);
-            }
-            uint32_t inc = local;
+                for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
+                    mine[q] = cnt[tid * (SS_BINS / SS_THREADS) + q];
+                    local += mine[q];
+                    fullest = max(fullest, mine[q]);
+                }
+                uint32_t inc = local;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((tid & 31) >= (uint32_t)d) inc += o;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if ((tid & 31) >= (uint32_t)d) inc += o;
+                }
+                if ((tid & 31) == 31) r32[tid >> 5] = inc;
+                __syncthreads();
+                before = inc - local;
+                for (uint32_t wq = 0; wq < (tid >> 5); ++wq) before += r32[wq];
+                __syncthreads();
+                fullest = block_reduce_ss(fullest, OpMaxU32(), 0u, r32);
             }
-            if ((tid & 31) == 31) r32[tid >> 5] = inc;
-            __syncthreads();
-            uint32_t before = inc - local;
-            for (uint32_t wq = 0; wq < (tid >> 5); ++wq) before += r32[wq];
-            __syncthreads();
-            fullest = block_reduce_ss(fullest, OpMaxU32(), 0u, r32);
-            if (fullest <= SS_BIN_CROWD && n <= room) {
+            if (fits && fullest <= SS_BIN_CROWD) {
 #pragma unroll
                 for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
                     cnt[tid * (SS_BINS / SS_THREADS) + q] = before;      // start of the bin; the scatter turns it into its end
