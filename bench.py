@@ -285,7 +285,8 @@ def run_b200_arm(args):
             self.canon = torch.empty(words, dtype=torch.int32, device=dev)
             self.launches = 0
 
-        def count(self, allreduce, ev=None):
+        def accumulate(self, ev=None):
+            """zero + pack + mark + swga_count_accumulate: this rank's additive table block"""
             self.fwd.zero_()
             _lib.check(lib.swga_pack(ctx.h, P(self.ascii), self.n, 0 if self.mode_b else 1, P(self.packed), P(self.brk), None))
             k = 1
@@ -297,22 +298,29 @@ def run_b200_arm(args):
             _lib.check(lib.swga_count_accumulate(ctx.h, P(self.packed), P(self.brk), self.n_starts, KMIN, KMAX, P(self.fwd), None))
             if ev is not None:
                 ev[1].record()
-            if allreduce and world > 1:
-                td.all_reduce(self.fwd, op=td.ReduceOp.SUM)
-            _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
-            _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
             # accumulate = k_bucket_hist (sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count
             # when the partitioned path applies (>= 2^22 starts, kmax 11 or 12), else the single k_count
             acc = 5 if (self.n_starts >= (1 << 22) and 8 <= 2 * KMAX - 14 <= 10) else 1
             self.launches = k + acc + (KMAX - KMIN) + 1
+
+        def finish(self):
+            """finalize + fold of the (allreduced) block"""
+            _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
+            _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
 
     fg = Dev(fg_seed, n_fg, fg_gc, fg_nrec, shard=False)
     bg = Dev(bg_seed, n_bg, bg_gc, bg_nrec, shard=True)
     torch.cuda.synchronize()
 
     def step(ev=None):
-        fg.count(allreduce=False)
-        bg.count(allreduce=True, ev=ev)
+        # the background's allreduce (NCCL, its own stream) runs while this rank counts the replicated foreground
+        bg.accumulate(ev)
+        work = td.all_reduce(bg.fwd, op=td.ReduceOp.SUM, async_op=True) if world > 1 else None
+        fg.accumulate()
+        fg.finish()
+        if work is not None:
+            work.wait()
+        bg.finish()
 
     def barrier():
         torch.cuda.synchronize()
