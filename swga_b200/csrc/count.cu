@@ -167,6 +167,39 @@ k_fold(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int kmin,
     canon[i] = c;
 }
 
+// The same for ONE large table (k >= 7), as a tiled transpose: a code is [A: 3 digits][M: k-6 digits][B: 3 digits]
+// and its reverse complement [rc(B)][rc(M)][rc(A)], so the block of middle value M (M <= rc(M)) loads the two
+// 64 x 64 tiles (.., M, ..) and (.., rc(M), ..) with coalesced 256-byte rows and finds every partner in shared
+// memory.  k_fold reads the partner of every code with a stride of 4^(k-1) words: one sector per lane.
+__global__ void __launch_bounds__(256)
+k_fold_tiled(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int k)
+{
+    __shared__ uint32_t t1[64][65], t2[64][65];
+    const int md = k - 6, sh = 2 * (k - 3);
+    const uint32_t M = blockIdx.x, rM = md ? rc_code(M, md) : 0u;
+    if (M > rM) return;                                        // handled by the block of rc(M)
+    const bool self = M == rM;
+    for (uint32_t i = threadIdx.x; i < 4096; i += 256) {
+        const uint32_t A = i >> 6, B = i & 63;
+        t1[A][B] = fwd[((uint64_t)A << sh) | (M << 6) | B];
+        if (!self) t2[A][B] = fwd[((uint64_t)A << sh) | (rM << 6) | B];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 4096; i += 256) {
+        const uint32_t A = i >> 6, B = i & 63, rA = rc_code(A, 3), rB = rc_code(B, 3);
+        {
+            const uint32_t x = (A << sh) | (M << 6) | B, r = (rB << sh) | (rM << 6) | rA;
+            const uint32_t v = t1[A][B], pv = self ? t1[rB][rA] : t2[rB][rA];
+            canon[x] = x < r ? v + pv : (x == r ? v : 0u);
+        }
+        if (!self) {
+            const uint32_t x = (A << sh) | (rM << 6) | B, r = (rB << sh) | (M << 6) | rA;
+            const uint32_t v = t2[A][B], pv = t1[rB][rA];
+            canon[x] = x < r ? v + pv : (x == r ? v : 0u);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // synthetic genome generator, bit-identical to swga_b200/synth.py
 // ------------------------------------------------------------------------------------------------
@@ -348,9 +381,16 @@ extern "C" int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint
 {
     ARG_CHECK(ctx && d_fwd && d_canon && d_fwd != d_canon);
     TRY(check_k(kmin, kmax));
-    const uint64_t total = swga_tables_words(kmin, kmax);
-    k_fold<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, kmax, swga_make_offs(kmin, kmax),
-                                                               total);
+    const TableOffs offs = swga_make_offs(kmin, kmax);
+    // small tables: one thread per code; tables of k >= 10 (94 % of the codes for 5..12): tiled transpose
+    const int k_split = std::max(kmin, 10);
+    if (kmin < k_split) {
+        const int k_hi = std::min(kmax, k_split - 1);
+        const uint64_t total = swga_tables_words(kmin, k_hi);
+        k_fold<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, k_hi, offs, total);
+    }
+    for (int k = k_split; k <= kmax; ++k)
+        k_fold_tiled<<<1u << (2 * (k - 6)), 256, 0, as_stream(stream)>>>(d_fwd + offs.off[k], d_canon + offs.off[k], k);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
