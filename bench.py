@@ -359,9 +359,9 @@ def run_b200_arm(args):
     acc = [0.0, 0.0, 0.0]
     n_st = max(3, min(args.steps, 10))
     for _ in range(n_st):
-        step()
+        bg.accumulate()
         st = (ctypes.c_float * 3)()
-        _lib.check(lib.swga_count_stage_ms(ctx.h, st))      # waits for the bg count of this step
+        _lib.check(lib.swga_count_stage_ms(ctx.h, st))      # waits for this background count
         for i in range(3):
             acc[i] += st[i] / n_st
     _lib.check(lib.swga_ctx_set_stage_timing(ctx.h, 0))
