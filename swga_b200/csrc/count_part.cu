@@ -10,9 +10,9 @@
 //   (2) k_bucket_layout turns the sample into (a) a global bucket layout -- estimated size + slack per
 //       bucket -- and (b) per-tile slot ranges inside the shared-memory staging area of k_partition;
 //   (3) k_partition     one tile = 16 Ki starts: every element takes its staging slot with ONE shared
-//       atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the tile's
-//       bucket runs are then copied to the buckets in coalesced pieces (one global atomicAdd per
-//       bucket and tile reserves the range);
+//       atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the whole
+//       16-byte chunks of every bucket's run are then copied to the bucket (one global atomicAdd per
+//       bucket and tile reserves the range), the up to 7 elements left over wait for the next tile;
 //   (4) k_bucket_count  shared-memory histogram of each bucket, added to T_kmax.
 //
 // Nothing depends on the sample being right: an element that finds its staging range full goes through
