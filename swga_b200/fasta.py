@@ -72,10 +72,14 @@ def parse_fasta_bytes(data, path=None, pin=False):
 
 
 def read_fasta(path, pin=False):
-    """Read a (plain-text) FASTA file.  gzip input, which DSK accepts through zlib, is not."""
+    """Read a FASTA file, plain or gzip-compressed (DSK opens its input through zlib's gzopen, which reads
+    both: ext/dsk/minia/Bank.cpp:39,275)."""
     with open(path, "rb") as f:
         magic = f.read(2)
     if magic == b"\x1f\x8b":
-        raise ValueError("%s is gzip-compressed; decompress it first" % path)
-    data = np.fromfile(path, dtype=np.uint8)
+        import gzip
+        with gzip.open(path, "rb") as f:
+            data = np.frombuffer(f.read(), dtype=np.uint8)
+    else:
+        data = np.fromfile(path, dtype=np.uint8)
     return parse_fasta_bytes(data, path=os.path.abspath(path), pin=pin)

@@ -77,6 +77,18 @@ def test_fasta_reader_matches_oracle_reader(lib, oracle):
     assert g.names == ["record1", "r2"]
 
 
+def test_gzip_fasta_is_read_like_plain(tmp_path):
+    """DSK opens its input with gzopen (Bank.cpp:39), which reads plain and gzip files alike."""
+    import gzip
+    from swga_b200 import fasta
+    data = b">a x\nACGTN\nacgt\n>b\nGG\n"
+    (tmp_path / "p.fa").write_bytes(data)
+    with gzip.open(str(tmp_path / "z.fa.gz"), "wb") as f:
+        f.write(data)
+    p, z = fasta.read_fasta(str(tmp_path / "p.fa")), fasta.read_fasta(str(tmp_path / "z.fa.gz"))
+    assert np.array_equal(p.seq, z.seq) and np.array_equal(p.rec_starts, z.rec_starts) and p.names == z.names == ["a", "b"]
+
+
 def test_dsk_file_roundtrip(lib, oracle, tmp_path):
     from swga_b200 import _lib, kmers
     k = 6
