@@ -426,25 +426,22 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
 }
 
 // ---- work items of phase 4: ceil(size_b / BC_ITEM) per bucket ----------------------------------------
-__global__ void k_item_prefix(const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ cursor, uint32_t nb,
-                              uint32_t *__restrict__ item_prefix)
+__global__ void __launch_bounds__(1024)
+k_item_prefix(const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ cursor, uint32_t nb,
+              uint32_t *__restrict__ item_prefix)
 {
-    // single block; nb <= 1024
-    __shared__ uint32_t s[1025];
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+    // single block of 1024 threads; nb <= 1024
+    __shared__ unsigned long long s_warp[33];
+    const uint32_t b = threadIdx.x;
+    unsigned long long items = 0;
+    if (b < nb) {
         const uint32_t sz = min(cursor[b], bucket_base[b + 1]) - bucket_base[b];
-        s[b] = (sz + BC_ITEM - 1) / BC_ITEM;
+        items = (sz + BC_ITEM - 1) / BC_ITEM;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (uint32_t b = 0; b < nb; ++b) {
-            const uint32_t c = s[b];
-            item_prefix[b] = run;
-            run += c;
-        }
-        item_prefix[nb] = run;
-    }
+    unsigned long long total;
+    const unsigned long long before = block_excl_scan_1024(items, s_warp, &total);
+    if (b < nb) item_prefix[b] = (uint32_t)before;
+    if (b == 0) item_prefix[nb] = (uint32_t)total;
 }
 
 // ---- (4) shared-memory histogram of each bucket, added to the top table ------------------------------
