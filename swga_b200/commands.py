@@ -57,22 +57,43 @@ def default_parameters(fg_length, bg_length):
 
 # ---------------------------------------------------------------------------------------------- init
 
+def fasta_len_quick(fasta_fp):
+    """commands/init.py:196-209: the reference's genome "length" is `grep -v '>' file | wc -c`, i.e. the bytes
+    of every line that contains no '>' PLUS one newline per such line.  These numbers, not
+    the base counts, feed min_fg_bind / max_bg_bind, set_finder's --bg_len and calculate_bg_dist_mean."""
+    import mmap
+    import re
+    size = os.path.getsize(fasta_fp)
+    if size == 0:
+        return 0
+    with open(fasta_fp, "rb") as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            total = size + (0 if mm[size - 1:size] == b"\n" else 1)      # grep terminates the last line
+            for m in re.finditer(rb"[^\n]*>[^\n]*(?:\n|$)", mm):
+                total -= (m.end() - m.start()) + (0 if mm[m.end() - 1:m.end()] == b"\n" else 1)
+        finally:
+            mm.close()
+    return total
+
+
 def init(fg_genome_fp, bg_genome_fp, exclude_fp=None, db_name=workspace.DEFAULT_DB_FNAME, force=False):
     """commands/init.py: record the genomes and their lengths; returns the default parameters."""
     if os.path.isfile(db_name):
         if not force:
             raise CommandError("Existing workspace %s: pass force=True to overwrite" % db_name)
         os.remove(db_name)
-    fg, bg = fasta.read_fasta(fg_genome_fp), fasta.read_fasta(bg_genome_fp)
+    fg = fasta.read_fasta(fg_genome_fp)                           # also validates the file (fasta_stats)
+    fg_length, bg_length = fasta_len_quick(fg_genome_fp), fasta_len_quick(bg_genome_fp)
     with workspace.Workspace(db_name) as ws:
         ws.create_tables()
         ws.metadata = dict(version=workspace.VERSION, fg_file=os.path.abspath(fg_genome_fp),
                            bg_file=os.path.abspath(bg_genome_fp),
                            ex_file=os.path.abspath(exclude_fp) if exclude_fp else None,
-                           fg_length=int(fg.n_bases), bg_length=int(bg.n_bases))
-    message("Foreground filepath: {}\n  Length:  {} bp\n  Records: {}".format(fg_genome_fp, fg.n_bases, fg.n_records))
-    message("Background filepath: {}\n  Length:  {} bp".format(bg_genome_fp, bg.n_bases))
-    return default_parameters(int(fg.n_bases), int(bg.n_bases))
+                           fg_length=fg_length, bg_length=bg_length)
+    message("Foreground filepath: {}\n  Length:  {} bp\n  Records: {}".format(fg_genome_fp, fg_length, fg.n_records))
+    message("Background filepath: {}\n  Length:  {} bp".format(bg_genome_fp, bg_length))
+    return default_parameters(fg_length, bg_length)
 
 
 # ---------------------------------------------------------------------------------------------- count
@@ -125,12 +146,13 @@ def _count_specific(ws, meta, input_fp):
         fg = kmers.count_kmers(k, meta["fg_file"], OUTPUT_DIR, 1)
         bg = kmers.count_kmers(k, meta["bg_file"], OUTPUT_DIR, 1)
         for mer in mers:
-            # primer_dict(mer, fg, bg, 0, INF, INF) (count.py:51-56,117-135): the dicts hold canonical k-mers
-            key = mer if mer in fg else locate.revcomp(mer)
-            if key not in fg:
+            # primer_dict(mer, fg, bg, 0, INF, INF) (count.py:51-56,117-135).  The dicts hold DSK-canonical k-mers
+            # only, so -- as in the reference -- a listed primer whose OTHER strand is the canonical one is
+            # reported missing and skipped, and only the canonical string is looked up in bg.
+            if mer not in fg:
                 message("{} does not exist in foreground genome, skipping...".format(mer))
                 continue
-            f_, b_ = fg[key], bg.get(key, bg.get(locate.revcomp(key), 0))
+            f_, b_ = fg[mer], bg.get(mer, 0)
             rows.append(dict(seq=mer, fg_freq=f_, bg_freq=b_, ratio=(f_ / float(b_)) if b_ > 0 else float("inf")))
     return ws.add_primers(rows, add_revcomp=False)
 

@@ -24,7 +24,13 @@ def test_commands_end_to_end(ws_dir, oracle):
     db = str(ws_dir / "primers.db")
     fg, bg = str(ws_dir / "fg.fa"), str(ws_dir / "bg.fa")
     params = commands.init(fg, bg, db_name=db)
-    assert params["count"]["min_fg_bind"] == int(1e-5 * 300_000) and params["count"]["max_bg_bind"] == int(6.7e-6 * 3_000_000)
+    # lengths as the reference takes them (init.py:196-209): grep -v '>' | wc -c = bases + one newline per line
+    import subprocess
+    fg_len, bg_len = (int(subprocess.check_output("grep -v '>' %s | wc -c" % f, shell=True)) for f in (fg, bg))
+    assert fg_len > 300_000 and bg_len > 3_000_000
+    with workspace.connection(db) as ws:
+        assert ws.metadata["fg_length"] == fg_len and ws.metadata["bg_length"] == bg_len
+    assert params["count"]["min_fg_bind"] == int(1e-5 * fg_len) and params["count"]["max_bg_bind"] == int(6.7e-6 * bg_len)
     with pytest.raises(commands.CommandError):
         commands.init(fg, bg, db_name=db)                                # existing workspace, no force
 
@@ -72,7 +78,7 @@ def test_commands_end_to_end(ws_dir, oracle):
     assert sorted(by_id) == list(range(1, len(by_id) + 1))               # Primers.assign_ids
     assert [r["_id"] for r in sets_db] == list(range(1, len(found) + 1))
     from swga_b200 import sets
-    gen = sets.find(min_bg_bind_dist=2000, min_size=2, max_size=3, bg_length=3_000_000, graph_fp=graph)
+    gen = sets.find(min_bg_bind_dist=2000, min_size=2, max_size=3, bg_length=bg_len, graph_fp=graph)
     passed = []
     for line in gen:
         ids, bgm = oracle.read_set_finder_line(line)
@@ -94,8 +100,33 @@ def test_commands_end_to_end(ws_dir, oracle):
     # ---- score: a user-defined set, never rejected, stored under a negative id
     seqs = [by_id[1].seq, by_id[2].seq, by_id[3].seq]
     out = commands.score_set(db_name=db, primers=seqs, force=True)
-    bgm = oracle.calculate_bg_dist_mean([by_id[i].bg_freq for i in (1, 2, 3)], 3_000_000)
+    bgm = oracle.calculate_bg_dist_mean([by_id[i].bg_freq for i in (1, 2, 3)], bg_len)
     sc, var, md = oracle.score_set([by_id[i].locations for i in (1, 2, 3)], 0, bgm, ends, interactive=True)
     assert out["_id"] == -1 and out["fg_max_dist"] == md and out["score"] == pytest.approx(sc, rel=1e-12)
     out2 = commands.score_set(db_name=db, primers=[by_id[4].seq, by_id[5].seq], force=True)
     assert out2["_id"] == -2
+
+
+def test_count_input_adds_listed_primers_like_the_reference(ws_dir, oracle, tmp_path):
+    """`swga count --input FILE` (count.py:29-68): listed k-mers are looked up in the DSK-canonical dicts only
+    (a primer whose other strand is canonical is skipped), existing ones are skipped, no reverse complements."""
+    from swga_b200 import commands, workspace
+    db = str(tmp_path / "p2.db")
+    fg, bg = str(ws_dir / "fg.fa"), str(ws_dir / "bg.fa")
+    commands.init(fg, bg, db_name=db)
+    fgd, bgd = open(fg, "rb").read(), open(bg, "rb").read()
+    f7, b7 = oracle.count_kmers_dict(fgd, 7), oracle.count_kmers_dict(bgd, 7)
+    canon = sorted(f7)[:3]
+    other = next(oracle.revcomp(s) for s in sorted(f7)[3:] if oracle.revcomp(s) not in f7)   # non-canonical strand
+    lst = tmp_path / "primers.txt"
+    lst.write_text("\n".join(canon + [other]) + "\n")
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))                                              # the DSK cache goes to ./.swga_tmp
+    try:
+        assert commands.count(db_name=db, input=str(lst)) == 3
+        assert commands.count(db_name=db, input=str(lst)) == 0           # all known (or skipped) now
+    finally:
+        os.chdir(cwd)
+    with workspace.connection(db) as ws:
+        got = {p.seq: (p.fg_freq, p.bg_freq) for p in ws.primers()}
+    assert got == {s: (f7[s], b7.get(s, 0)) for s in canon}
