@@ -95,3 +95,68 @@ def test_filter_and_find_sets_match_oracle(workspace, oracle):
                                 score_expression="fg_max_dist / set_size")
     for row in found2:
         assert row["score"] == row["fg_max_dist"] // row["set_size"]       # Python-2 integer division
+
+
+def test_config5_full_size(oracle, tmp_path):
+    """BASELINE config 5 at its real size: synthetic 1.3 Mbp foreground (Wolbachia-sized) vs 140 Mbp background
+    (Drosophila-sized, 6 records -> DSK mode B), full count -> filter -> locate -> find_sets with the host
+    set_finder, the reference's default parameters.  Counting is compared bit for bit with the oracle's dense
+    tables (the 140 Mbp background takes the partitioned kernel), the rest with the oracle's replay."""
+    import torch
+    from swga_b200 import fasta, kmers, locate, pipeline, sets, synth
+    genomes = {}
+    for name in ("C5_fg", "C5_bg"):
+        seed, n, gc, n_rec = synth.CONFIGS[name]
+        seq = synth.bases(seed, 0, n, gc)
+        rs = synth.equal_records(n, n_rec)
+        g = fasta.Genome(seq, rs, ["%s_r%d" % (name, i + 1) for i in range(n_rec)])
+        genomes[name] = g
+        d = torch.from_numpy(seq).cuda()
+        _, canon = kmers.count_all_device(d, rs, mode_b=g.dsk_mode_b)
+        torch.cuda.synchronize()
+        want = oracle.count_dense_allk(seq, rs, 5, 12, mode_b=int(g.dsk_mode_b))
+        assert np.array_equal(canon.cpu().numpy().view(np.uint32), want), name
+        del d, canon, want
+    fg, bg = genomes["C5_fg"], genomes["C5_bg"]
+    assert bg.dsk_mode_b and fg.dsk_mode_b                       # one record of 1.3 Mbp > 1,000,000 as well
+    min_fg_bind, max_bg_bind = int(1e-5 * fg.n_bases), int(6.7e-6 * bg.n_bases)
+    rows = pipeline.count_primers(fg, bg, None, min_size=5, max_size=12, min_fg_bind=min_fg_bind,
+                                  max_bg_bind=max_bg_bind, max_dimer_bp=3)
+    assert len(rows) > 1000
+    primers = [pipeline.Primer(r["seq"], r["fg_freq"], r["bg_freq"], r["ratio"]) for r in rows]
+    gi = locate.GenomeIndex(fg)
+    active = pipeline.filter_primers(primers, gi, min_fg_bind=min_fg_bind, max_bg_bind=max_bg_bind, max_primers=200,
+                                     max_gini=0.6)
+    assert 20 < len(active) <= 200
+    recs = [(fg.names[r], fg.seq[int(fg.rec_starts[r]):int(fg.rec_starts[r + 1])].tobytes().decode("latin-1"))
+            for r in range(fg.n_records)]
+    ends = oracle.chromosome_ends(recs)
+    for p in active[:40]:
+        loc = oracle.binding_sites(p.seq, recs)
+        assert p.locations == loc and sum(len(v) for v in loc.values()) == p.fg_freq
+        assert p.gini == oracle.gini(oracle.seq_diff(oracle.linearize_binding_sites([loc], ends)))
+    graph = str(tmp_path / "c5.dimacs")
+    found = pipeline.find_sets(active, gi, int(bg.n_bases), min_bg_bind_dist=30000, max_fg_bind_dist=36000, min_size=2,
+                               max_size=7, max_dimer_bp=3, max_sets=10, graph_fp=graph)
+    by_id = {p._id: p for p in active}
+    assert 0 < len(found) <= 10
+    # every stored set is what the oracle computes for the same primers, and it passes the filter
+    for row in found:
+        sc, var, md = oracle.score_set([by_id[i].locations for i in row["primer_ids"]], 36000, row["bg_dist_mean"], ends)
+        assert sc is not False and row["fg_max_dist"] == md
+        assert row["fg_dist_mean"] == var["fg_dist_mean"] and row["fg_dist_gini"] == var["fg_dist_gini"]
+        assert row["score"] == pytest.approx(sc, rel=1e-12)
+    # ... and they are the FIRST passing sets of the set_finder stream: replay its first lines through the oracle
+    gen = sets.find(min_bg_bind_dist=30000, min_size=2, max_size=7, bg_length=int(bg.n_bases), graph_fp=graph)
+    head, oracle_pass = [], []
+    for line in gen:
+        ids, bgm = oracle.read_set_finder_line(line)
+        head.append(tuple(ids))
+        sc, var, md = oracle.score_set([by_id[i].locations for i in ids], 36000, bgm, ends)
+        if sc is not False:
+            oracle_pass.append(tuple(ids))
+        if len(head) >= 1500 or len(oracle_pass) >= 10:
+            break
+    gen.close()
+    in_head = set(head)
+    assert [tuple(r["primer_ids"]) for r in found if tuple(r["primer_ids"]) in in_head][:len(oracle_pass)] == oracle_pass
