@@ -283,3 +283,45 @@ def test_scoring_kernels_edge_shapes(oracle):
                         assert float(res.fg_dist_gini[i]) == oracle.gini(gaps), (cap, i)
     finally:
         _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
+
+
+def test_config3_config4_full_size(oracle):
+    """BASELINE configs 3 and 4 at their real size: the synthetic 23 Mbp AT-rich foreground in 14 records is counted
+    (bit-exact vs the oracle), the C4 primers (its 200 most frequent 8..12-mers, ~25,000 sites each) are located and
+    a sample of the C4 candidate sets (6-10 primers, ~196,000 unique sites: the dense kernel) is scored; sites and
+    statistics are compared with the oracle's restatement of locate.py / stats.py."""
+    import torch
+    from swga_b200 import fasta, kmers, locate, score, synth, workloads
+    seed, n, gc, n_rec = synth.CONFIGS["C3_fg"]
+    seq = synth.bases(seed, 0, n, gc)
+    rs = synth.equal_records(n, n_rec)
+    g = fasta.Genome(seq, rs, ["chr%d" % (i + 1) for i in range(n_rec)])
+    tabs = kmers.count_all(g, 5, 12)
+    want = oracle.count_dense_allk(seq, rs, 5, 12, mode_b=int(g.dsk_mode_b))
+    assert np.array_equal(np.concatenate([tabs.table(k) for k in range(5, 13)]), want)
+    prim = workloads.top_primers(tabs, 5, 12, 200)
+    seqs = [kmers.codes_to_kmers([c], k)[0] for k, c, _ in prim]
+    gi = locate.GenomeIndex(g)
+    sl = score.SiteLists.from_index(gi, seqs)
+    S = 12
+    sets_, m = workloads.c4_sets(S)
+    bgs = np.full(S, 1234.5)
+    res = score.score_sets(sl, sets_, bgs, 36000)
+    recs = records_of(g)
+    ends = oracle.chromosome_ends(recs)
+    locs = {}
+    for s in range(S):
+        ids = [int(x) for x in sets_[s] if x >= 0]
+        for i in ids:
+            if i not in locs:
+                locs[i] = oracle.binding_sites(seqs[i], recs)
+                assert gi.binding_sites(seqs[i]) == locs[i]                  # kernel (c) at full size
+        lin = oracle.linearize_binding_sites([locs[i] for i in ids], ends)
+        gaps = oracle.seq_diff(lin)
+        assert int(res.n_sites[s]) == len(lin) and int(res.fg_max_dist[s]) == max(gaps)
+        assert float(res.fg_dist_mean[s]) == oracle.mean(gaps)
+        assert float(res.fg_dist_std[s]) == pytest.approx(oracle.stdev(gaps), rel=1e-12)
+        assert bool(res.passed[s]) == (max(gaps) <= 36000)
+        if res.passed[s]:
+            assert float(res.fg_dist_gini[s]) == oracle.gini(gaps)
+            assert float(res.score[s]) == pytest.approx(oracle.mean(gaps) * oracle.gini(gaps) / 1234.5, rel=1e-12)
