@@ -496,6 +496,28 @@ def run_b200_arm(args):
                 ok &= bool((diff >= 0).all()) and int(diff.sum()) == bg_nrec
         props = {"bg_tables_sum_and_marginals_ok": bool(ok)}
 
+    # ---- the count -> primer-row merge of `swga count` on the tables just built (BASELINE config 2: count + filter) ----
+    merge = None
+    if rank == 0 and not args.no_extras:
+        cap = 1 << 22
+        rows = torch.empty(cap * 4, dtype=torch.int32, device=dev)
+        n_rows = torch.zeros(1, dtype=torch.int32, device=dev)
+        min_fg, max_bg = int(1e-5 * n_fg), int(6.7e-6 * n_bg)         # the defaults `swga init` derives (init.py:34-35)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(3):
+            n_rows.zero_()
+            f0.record()
+            _lib.check(lib.swga_filter_primers(ctx.h, P(fg.canon), P(bg.canon), None, KMIN, KMAX, min_fg, max_bg, 3, 1,
+                                               P(rows), cap, P(n_rows), None))
+            f1.record()
+            torch.cuda.synchronize()
+            ms = f0.elapsed_time(f1)
+            best = ms if best is None else min(best, ms)
+        merge = {"kernel": "k_filter_primers", "ms": best, "rows": int(n_rows.item()), "min_fg_bind": min_fg,
+                 "max_bg_bind": max_bg, "max_dimer_bp": 3, "codes_tested": int(words)}
+        del rows
+
     scoring = None
     if rank == 0 and not args.no_extras:
         try:
@@ -520,7 +542,7 @@ def run_b200_arm(args):
                        if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
             "roofline": roofline, "path_roofline": path, "atomic": atomic, "cpu_baseline": cpu, "e2e": e2e,
             "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps, "numa_node": numa,
-            "scoring": scoring, "full_size_properties": props,
+            "scoring": scoring, "count_merge": merge, "full_size_properties": props,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
