@@ -1,0 +1,59 @@
+"""The reference's own known-answer tests for the host remainder of the path, run against swga_b200's host
+code (no GPU): heterodimer graph (swga/tests/test_graph.py:28-51), DIMACS output (test_find_sets_cmd.py:18-30),
+the set_finder protocol (test_find_sets_cmd.py:33-61, test_score.py:4-7) and the golden set_finder stream."""
+import json
+import os
+
+import pytest
+
+from swga_b200 import pipeline, score, sets
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def P(_id, seq, **kw):
+    p = pipeline.Primer(seq, kw.get("fg_freq", 0), kw.get("bg_freq", 0), kw.get("ratio", 0.0))
+    p._id = _id
+    return p
+
+
+def test_reference_graph_kats():
+    ref = P(0, "ATGCTC")
+    for seq in ("CAGCAT", "GAGGTA", "ATCGAG"):                           # heterodimers: no edge
+        assert pipeline.build_edges([ref, P(1, seq)], 2) == []
+    assert pipeline.build_edges([ref, P(4, "TTCCAC")], 2) == [[0, 4]]    # valid pair
+    assert pipeline.build_edges([ref, P(5, "ATGC")], 2) == []            # subsequence
+
+
+def test_reference_build_graph_kat(tmp_path):
+    primers = [P(None, "ATGC", fg_freq=1, bg_freq=2, ratio=1.0), P(None, "GGCC", fg_freq=1, bg_freq=3, ratio=0.5),
+               P(None, "CCTA", fg_freq=2, bg_freq=0, ratio=float("inf"))]
+    out = tmp_path / "graph"
+    pipeline.build_graph(primers, 3, str(out))
+    # ids by ratio descending (primers.py:255-268); vertex weight = bg_freq or 1 (graph.py:45-52)
+    assert out.read_text() == "p sp 3 3\nn 1 1\nn 2 2\nn 3 3\ne 1 2\ne 1 3\ne 2 3\n"
+
+
+def test_reference_set_finder_kat(tmp_path):
+    try:
+        sets.set_finder()
+    except IOError:
+        pytest.skip("set_finder binary not built (needs the reference sources at build time)")
+    graph = ("p sp 6 7\nn 1 1\nn 2 2\nn 3 1\nn 4 4\nn 5 5\nn 6 6\n"
+             "e 1 2\ne 1 3\ne 2 3\ne 2 4\ne 4 5\ne 4 6\ne 5 6\n")
+    fp = tmp_path / "testgraph"
+    fp.write_text(graph)
+    gen = sets.find(min_bg_bind_dist=2, min_size=3, max_size=3, bg_length=10, graph_fp=str(fp))
+    output = list(gen)
+    assert len(output) == 1
+    ids, bg_dist_mean = score.read_set_finder_line(output[0])
+    assert ids == [1, 2, 3] and bg_dist_mean == 2.5
+    with open(os.path.join(GOLDEN, "set_finder_golden.json")) as f:
+        gold = json.load(f)
+    assert gold["graph"] == graph
+
+
+def test_read_set_finder_line_kat():
+    assert score.read_set_finder_line("1,2,3 1.5") == ([1, 2, 3], 1.5)   # swga/tests/test_score.py:4-7
+    with pytest.raises(ValueError):
+        score.read_set_finder_line("not a line")
