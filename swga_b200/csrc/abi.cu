@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -177,23 +178,26 @@ extern "C" int swga_stream_sync(swga_ctx *ctx, void *stream)
 //   * '+' at line start would switch the reference to FASTQ: rejected here
 static inline bool is_rec_start(uint8_t c) { return c == '>' || c == '@' || c == 0xFF; }
 
-extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uint64_t *h_rec_starts,
-                               uint64_t *h_hdr, uint64_t *n_bases, uint64_t *n_rec)
+// One contiguous range of LINES of the image, [pos, end) with pos at a line start.  `rec_len` enters as the
+// length of the record the range continues (only "0" versus "more" matters, for the '\r' rule).  With `fill`
+// the range writes its bytes at h_seq + base and its records from index rec0 on.
+struct ScanRange {
+    uint64_t pos = 0, end = 0;             // in: byte range
+    uint64_t rec_len_in = 0;               // in: 0 = the previous non-empty line is a header (or there is none)
+    uint64_t bases = 0, recs = 0;          // out of the counting pass; in for the filling pass as prefix sums
+    uint64_t base0 = 0, rec0 = 0;
+    int status = SWGA_OK;
+    uint64_t bad_pos = 0;
+};
+
+static void scan_range(const uint8_t *f, ScanRange &r, uint8_t *h_seq, uint64_t *h_rec_starts, uint64_t *h_hdr)
 {
-    ARG_CHECK((f || n == 0) && n_bases && n_rec);
     const bool fill = h_seq != nullptr || h_rec_starts != nullptr;
-    uint64_t total = 0, rec = 0;
-    if (n > 0 && f[0] != '>' && f[0] != '@') {
-        swga_set_error("not a FASTA image: first byte is 0x%02x, expected '>' (DSK would read it as a list of file names)",
-                       f[0]);
-        return SWGA_E_FORMAT;
-    }
-    uint64_t pos = 0;
-    uint64_t rec_len = 0;
-    while (pos < n) {
+    uint64_t total = r.base0, rec = r.rec0, rec_len = r.rec_len_in, pos = r.pos;
+    while (pos < r.end) {
         const uint8_t c = f[pos];
-        const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + pos, '\n', n - pos));
-        const uint64_t eol = nl ? (uint64_t)(nl - f) : n;      // index of '\n' or n
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + pos, '\n', r.end - pos));
+        const uint64_t eol = nl ? (uint64_t)(nl - f) : r.end;  // index of '\n' or the end of the range (= end of file)
         if (is_rec_start(c)) {
             if (fill && h_rec_starts) h_rec_starts[rec] = total;
             if (fill && h_hdr) {
@@ -206,21 +210,111 @@ extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uin
             rec++;
             rec_len = 0;
         } else if (c == '+') {
-            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported", (unsigned long long)pos);
-            return SWGA_E_FORMAT;
+            r.status = SWGA_E_FORMAT;
+            r.bad_pos = pos;
+            return;
         } else if (eol > pos) {
             const uint64_t len = eol - pos;
-            if (h_seq) memcpy(h_seq + total, f + pos, len);
-            total += len;
             rec_len += len;
-            if (rec_len > 1 && f[eol - 1] == '\r') {
-                total--;
-                rec_len--;
-            }
+            // one trailing '\r' is dropped -- except for a last line of exactly one byte without a newline: the
+            // reference has taken that byte with getc and its gets() returns at end of file before the rule
+            // (Bank.cpp:80-81,124-125).  Decided BEFORE the copy: the byte after this line's share of h_seq
+            // belongs to the next line, which another thread may be writing.
+            const uint64_t drop = (rec_len > 1 && f[eol - 1] == '\r' && !(nl == nullptr && len == 1)) ? 1 : 0;
+            if (h_seq) memcpy(h_seq + total, f + pos, len - drop);
+            total += len - drop;
+            rec_len -= drop;
         }
         pos = eol + 1;
     }
-    if (fill && h_rec_starts) h_rec_starts[rec] = total;
+    r.bases = total - r.base0;
+    r.recs = rec - r.rec0;
+}
+
+// Both passes (sizes, then fill) run on up to 16 host threads: the image is cut at line starts into ranges that
+// are scanned independently (a line never depends on another one except through "is the record still empty",
+// which a range recovers by looking at the lines before its start), then prefix sums place every range.
+extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uint64_t *h_rec_starts,
+                               uint64_t *h_hdr, uint64_t *n_bases, uint64_t *n_rec)
+{
+    ARG_CHECK((f || n == 0) && n_bases && n_rec);
+    if (n > 0 && f[0] != '>' && f[0] != '@') {
+        swga_set_error("not a FASTA image: first byte is 0x%02x, expected '>' (DSK would read it as a list of file names)",
+                       f[0]);
+        return SWGA_E_FORMAT;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    const char *env_chunk = getenv("SWGA_FASTA_CHUNK");          // bytes per range at least (tests force small ranges)
+    const uint64_t per_thread_min = env_chunk && atoll(env_chunk) > 0 ? (uint64_t)atoll(env_chunk) : (8ull << 20);
+    const unsigned n_thr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(hw ? hw : 1, 16u), n / per_thread_min));
+    std::vector<ScanRange> rg(n_thr);
+    // cut points: the first line start at or after i * n / n_thr
+    std::vector<uint64_t> cut(n_thr + 1, n);
+    cut[0] = 0;
+    for (unsigned t = 1; t < n_thr; ++t) {
+        uint64_t p = std::max(cut[t - 1], n / n_thr * t);
+        if (p > 0 && p < n && f[p - 1] != '\n') {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + p, '\n', n - p));
+            p = nl ? (uint64_t)(nl - f) + 1 : n;
+        }
+        cut[t] = std::min(p, n);
+    }
+    for (unsigned t = 0; t < n_thr; ++t) {
+        rg[t].pos = cut[t];
+        rg[t].end = cut[t + 1];
+        // is the record that this range continues still empty?  walk back over the lines before the cut:
+        // empty lines do not count, a header line means "empty", any other line means "not empty"
+        uint64_t q = cut[t];
+        rg[t].rec_len_in = 0;
+        while (q > 0) {
+            uint64_t e = q - 1;                                // the '\n' that ends the previous line
+            uint64_t s0 = e;
+            while (s0 > 0 && f[s0 - 1] != '\n') --s0;          // start of that line
+            if (e > s0) {                                      // non-empty line
+                rg[t].rec_len_in = is_rec_start(f[s0]) ? 0 : 2;
+                break;
+            }
+            q = s0;
+        }
+    }
+    auto run = [&](uint8_t *seq, uint64_t *rs, uint64_t *hdr) {
+        if (n_thr == 1) {
+            scan_range(f, rg[0], seq, rs, hdr);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < n_thr; ++t) th.emplace_back([&, t] { scan_range(f, rg[t], seq, rs, hdr); });
+        for (auto &x : th) x.join();
+    };
+    // the sizes pass of the caller's first call (h_seq == NULL) is remembered for the filling call that follows
+    static thread_local const uint8_t *last_f = nullptr;
+    static thread_local uint64_t last_n = 0;
+    static thread_local std::vector<ScanRange> last_rg;
+    const bool filling = h_seq != nullptr || h_rec_starts != nullptr;
+    if (filling && last_f == f && last_n == n && last_rg.size() == rg.size()) {
+        rg = last_rg;
+    } else {
+        run(nullptr, nullptr, nullptr);                        // sizes
+    }
+    last_f = filling ? nullptr : f;
+    last_n = n;
+    if (!filling) last_rg = rg;
+    uint64_t total = 0, rec = 0;
+    for (unsigned t = 0; t < n_thr; ++t) {
+        if (rg[t].status != SWGA_OK) {
+            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
+                           (unsigned long long)rg[t].bad_pos);
+            return SWGA_E_FORMAT;
+        }
+        rg[t].base0 = total;
+        rg[t].rec0 = rec;
+        total += rg[t].bases;
+        rec += rg[t].recs;
+    }
+    if (h_seq != nullptr || h_rec_starts != nullptr) {
+        run(h_seq, h_rec_starts, h_hdr);                       // fill
+        if (h_rec_starts) h_rec_starts[rec] = total;
+    }
     *n_bases = total;
     *n_rec = rec;
     return SWGA_OK;

@@ -80,6 +80,8 @@ def read_fasta(path, pin=False):
         import gzip
         with gzip.open(path, "rb") as f:
             data = np.frombuffer(f.read(), dtype=np.uint8)
+    elif os.path.getsize(path) > 0:
+        data = np.memmap(path, dtype=np.uint8, mode="r")          # the reader's threads read the page cache directly
     else:
-        data = np.fromfile(path, dtype=np.uint8)
+        data = np.zeros(0, dtype=np.uint8)
     return parse_fasta_bytes(data, path=os.path.abspath(path), pin=pin)

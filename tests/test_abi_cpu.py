@@ -77,6 +77,28 @@ def test_fasta_reader_matches_oracle_reader(lib, oracle):
     assert g.names == ["record1", "r2"]
 
 
+def test_threaded_fasta_reader_equals_oracle_reader(lib, oracle, monkeypatch):
+    """The reader cuts the image at line starts into ranges scanned by up to 16 threads; with 1-byte ranges forced,
+    random images (headers, empty lines, CRLF, lone CR lines, long lines) must still parse like DSK's reader."""
+    from swga_b200 import fasta
+    rng = np.random.RandomState(99)
+    pieces = [b">h\n", b">h x y\n", b"@q\n", b"\n", b"\r\n", b"ACGT\n", b"ACGTNNAC\r\n", b"A\n", b"\r", b"acgtRYK\n",
+              b"G" * 300 + b"\n", b"TTTT", b">\n"]
+    monkeypatch.setenv("SWGA_FASTA_CHUNK", "1")
+    for it in range(300):
+        body = b"".join(pieces[i] for i in rng.randint(0, len(pieces), int(rng.randint(0, 40))))
+        data = b">first\n" + body
+        g = fasta.parse_fasta_bytes(data)
+        seq, rs = oracle.fasta_parse_dsk(data)
+        assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs), (it, data)
+    monkeypatch.setenv("SWGA_FASTA_CHUNK", "64")
+    big = b"".join([b">r%d d\n" % i + b"ACGTTGCA" * int(rng.randint(0, 40)) + b"\n" + b"GG\r\n" * int(rng.randint(0, 3))
+                    for i in range(400)])
+    g = fasta.parse_fasta_bytes(big)
+    seq, rs = oracle.fasta_parse_dsk(big)
+    assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs) and g.names[:2] == ["r0", "r1"]
+
+
 def test_gzip_fasta_is_read_like_plain(tmp_path):
     """DSK opens its input with gzopen (Bank.cpp:39), which reads plain and gzip files alike."""
     import gzip
