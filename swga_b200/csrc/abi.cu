@@ -79,6 +79,8 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
     }
     for (int i = 0; i < 4; ++i)
         if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     delete c;
@@ -383,14 +385,53 @@ extern "C" int swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
         TRY(swga_ensure(ctx, ctx->recs, (n_rec + 1) * 8));
         CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, h_rec_starts, (n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->s_comp));
     }
+    // A pageable source would make every cudaMemcpyAsync a synchronous, driver-staged copy (~9 GB/s measured):
+    // such buffers go through two pinned staging blocks of the context, filled by a few host threads while the
+    // previous chunk is on the bus.  (Pinning the caller's buffer instead costs ~0.45 s per GB.)
+    bool pinned = true;
+    {
+        cudaPointerAttributes attr;
+        const cudaError_t e = cudaPointerGetAttributes(&attr, h_seq);
+        if (e != cudaSuccess) cudaGetLastError();
+        pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
+    }
+    if (!pinned && n > 0) {
+        const size_t want = (size_t)cap + 64;
+        if (ctx->h_stage_cap < want) {
+            for (int i = 0; i < 2; ++i) {
+                if (ctx->h_stage[i]) CUDA_TRY(cudaFreeHost(ctx->h_stage[i]));
+                ctx->h_stage[i] = nullptr;
+                CUDA_TRY(cudaHostAlloc(&ctx->h_stage[i], want, cudaHostAllocDefault));
+            }
+            ctx->h_stage_cap = want;
+        }
+    }
     int it = 0;
     for (uint64_t a = 0; a < n_starts; a += CHUNK, ++it) {
         const int b = it & 1;
         const uint64_t e_starts = std::min(n_starts, a + CHUNK);   // owned starts [a, e_starts)
         const uint64_t e_bases = std::min(n, e_starts + (uint64_t)kmax - 1);
         const uint64_t len = e_bases - a;
+        const uint8_t *src = h_seq + a;
+        if (!pinned) {
+            CUDA_TRY(cudaEventSynchronize(ctx->ev_h2d[b]));     // the copy that last read this block (this call or an earlier one)
+            uint8_t *dst = (uint8_t *)ctx->h_stage[b];
+            const unsigned n_thr = len >= (8u << 20) ? 4u : 1u;
+            if (n_thr == 1) {
+                memcpy(dst, src, len);
+            } else {
+                std::vector<std::thread> th;
+                const uint64_t per = (len + n_thr - 1) / n_thr;
+                for (unsigned t = 0; t < n_thr; ++t) {
+                    const uint64_t lo = std::min<uint64_t>(len, t * per), hi = std::min<uint64_t>(len, lo + per);
+                    th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+                }
+                for (auto &x : th) x.join();
+            }
+            src = dst;
+        }
         if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));
-        CUDA_TRY(cudaMemcpyAsync(ctx->ascii[b].p, h_seq + a, len, cudaMemcpyHostToDevice, ctx->s_copy));
+        CUDA_TRY(cudaMemcpyAsync(ctx->ascii[b].p, src, len, cudaMemcpyHostToDevice, ctx->s_copy));
         CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
         CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
         uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;

@@ -86,7 +86,7 @@ def count_all(genome, kmin=DEFAULT_KMIN, kmax=DEFAULT_KMAX, device=None):
     lib = _lib.load()
     ctx = _lib.context(device)
     if not isinstance(genome, fasta.Genome):
-        genome = fasta.read_fasta(genome, pin=True)
+        genome = fasta.read_fasta(genome, pin=False)        # pageable: the library stages it (see swga_count_stream_host)
     words = int(lib.swga_tables_words(kmin, kmax))
     out = np.empty(words, dtype=np.uint32)
     rs = np.ascontiguousarray(genome.rec_starts, dtype=np.uint64)

@@ -37,18 +37,29 @@ def _message(msg):
 # ------------------------------------------------------------------------------ swga count
 
 def count_tables_device(genome, kmin, kmax, device=None):
-    """Canonical tables of one genome left on the device (int32 CUDA tensor)."""
+    """Canonical tables of one genome left on the device (int32 CUDA tensor).  The bases are streamed from the
+    host buffer in chunks (H2D overlapped with pack + count; a pageable buffer goes through the library's pinned
+    staging blocks, which is cheaper than pinning a genome-sized buffer for one pass)."""
     import torch
     if not isinstance(genome, fasta.Genome):
-        genome = fasta.read_fasta(genome, pin=True)
+        genome = fasta.read_fasta(genome, pin=False)
+    lib = _lib.load()
     ctx = _lib.context(device)
     dev = torch.device("cuda", ctx.device)
+    words = int(lib.swga_tables_words(kmin, kmax))
     with torch.cuda.device(dev):
-        d = torch.from_numpy(np.ascontiguousarray(genome.seq)).to(dev) if genome.n_bases else torch.zeros(
-            16, dtype=torch.uint8, device=dev)
-        if genome.n_bases == 0:
-            return torch.zeros(int(_lib.load().swga_tables_words(kmin, kmax)), dtype=torch.int32, device=dev)
-        _, canon = kmers.count_all_device(d, genome.rec_starts, genome.dsk_mode_b, kmin, kmax)
+        cs = torch.cuda.ExternalStream(lib.swga_ctx_compute_stream(ctx.h), device=dev)
+        with torch.cuda.stream(cs):
+            fwd = torch.zeros(words, dtype=torch.int32, device=dev)
+            canon = torch.zeros(words, dtype=torch.int32, device=dev)
+            if genome.n_bases:
+                rs = np.ascontiguousarray(genome.rec_starts, dtype=np.uint64)
+                _lib.check(lib.swga_count_stream_host(ctx.h, _lib.ptr(genome.seq), genome.n_bases, _lib.ptr(rs),
+                                                      genome.n_records, int(genome.dsk_mode_b), kmin, kmax,
+                                                      genome.n_bases, _lib.ptr(fwd)))
+                _lib.check(lib.swga_count_finalize(ctx.h, kmin, kmax, _lib.ptr(fwd), cs.cuda_stream))
+                _lib.check(lib.swga_fold_canonical(ctx.h, kmin, kmax, _lib.ptr(fwd), _lib.ptr(canon), cs.cuda_stream))
+        cs.synchronize()
     return canon
 
 
