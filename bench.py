@@ -575,6 +575,7 @@ def scoring_extra(dev):
         sl = score.SiteLists.from_index(gi, seqs)
         sets_, _ = workloads.c4_sets(S)
         mapped = np.where(sets_ >= 0, sl.list_of_primer[np.clip(sets_, 0, 199)], -1).astype(np.int32)
+        mapped_host = sets_
         d_sets = torch.from_numpy(mapped).to(dev)
         bg = torch.full((S,), 1000.0, dtype=torch.float64, device=dev)
         row = {"sets": S}
@@ -590,9 +591,18 @@ def scoring_extra(dev):
                 best = ms if best is None else min(best, ms)
             L = res.n_sites.cpu().numpy().view(np.uint32)
             st = res.status.cpu().numpy()
+            # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
+            h_bg = np.full(S, 1000.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            score.score_sets(sl, sets_, h_bg, max_fg)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
             row[label] = {"sets_per_s": S / best * 1e3, "ms": best, "mean_unique_sites_per_set": float(L.mean()),
                           "passed_frac": float((st & 1).mean()),
-                          "merged_sites_per_s": float(sl.counts()[:-1].mean()) * 8 * S / best * 1e3}
+                          "merged_sites_per_s": float(sl.counts()[:-1].mean()) * 8 * S / best * 1e3,
+                          "e2e_sets_per_s": S / e2e_s, "e2e_h2d_bytes": int(mapped_host.nbytes + h_bg.nbytes),
+                          "e2e_d2h_bytes": int(S * 41)}
         out[name] = row
     return out
 

@@ -208,8 +208,7 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
         sets = np.asarray(sets, dtype=np.int32)
         if sets.ndim != 2:
             raise ValueError("sets must be [S][max_m]")
-        mapped = np.where(sets >= 0, sl.list_of_primer[np.clip(sets, 0, max(sl.n_primers - 1, 0))], -1).astype(np.int32)
-        S, max_m = mapped.shape
+        S, max_m = sets.shape
     else:
         S, max_m = d_sets.shape
     mfd = max_fg_bind_dist
@@ -217,7 +216,13 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
         if d_sets is None:
-            d_sets = torch.from_numpy(np.ascontiguousarray(mapped)).to(dev)
+            # primer index -> list id on the device (identical primers share one list); -1 stays -1
+            d_raw = torch.from_numpy(np.ascontiguousarray(sets)).to(dev)
+            lop = getattr(sl, "_d_list_of_primer", None)
+            if lop is None:
+                lop = sl._d_list_of_primer = torch.from_numpy(
+                    np.ascontiguousarray(sl.list_of_primer if sl.n_primers else np.zeros(1), dtype=np.int32)).to(dev)
+            d_sets = torch.where(d_raw >= 0, lop[d_raw.clamp(0, max(sl.n_primers - 1, 0)).long()], d_raw.new_full((), -1))
         d_bg = bg_dist_mean if isinstance(bg_dist_mean, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(bg_dist_mean, dtype=np.float64)).to(dev)
         o_n = torch.empty(S, dtype=torch.int32, device=dev)
