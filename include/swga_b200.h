@@ -174,6 +174,14 @@ int swga_filter_primers(swga_ctx *ctx, const uint32_t *d_canon_fg, const uint32_
                         int64_t max_bg_bind, int max_dimer_bp, uint32_t exclude_threshold,
                         uint32_t *d_rows, uint32_t row_capacity, uint32_t *d_n_rows, void *stream);
 
+/* set_finder's stdout, a block at a time: what score.read_set_finder_line (swga/score.py:16-24) does per line
+ * ("id,id,... weight\n", set_finder.c:427-444) for every complete line of `text`, at most `cap` of them.
+ * h_ids [cap][max_m] (-1 padded), h_weight [cap], h_ok [cap] (0 = a line Python would reject, or more than
+ * max_m ids); *consumed = bytes of the complete lines parsed (an unfinished last line stays for the next block). */
+int swga_parse_set_lines(const char *text, uint64_t n_bytes, uint32_t max_m, uint64_t cap,
+                         int32_t *h_ids, double *h_weight, uint8_t *h_ok, uint64_t *n_lines,
+                         uint64_t *consumed);
+
 /* DSK result-file writer (ext/dsk/minia/SortingCount.cpp:149-156,649-653; read back by
  * swga/kmers.py:94-115): [i32 64][i32 k] then (u64 code, u32 count) for every count >= threshold. */
 int swga_write_dsk_file(const char *path, int k, const uint32_t *h_canon_k, uint32_t threshold,

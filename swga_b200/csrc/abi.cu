@@ -513,3 +513,72 @@ extern "C" int swga_write_dsk_file(const char *path, int k, const uint32_t *h_ca
     if (n_written) *n_written = cnt;
     return SWGA_OK;
 }
+
+// ---- set_finder output, a block at a time ------------------------------------------------------
+// What score.read_set_finder_line (swga/score.py:16-24) does per line -- `ids, w = line.strip('\n').split(' ');
+// [int(i) for i in ids.split(',')]; float(w)` -- for a whole block of stdout: the per-line Python of
+// FindSets.process_lines (commands/find_sets.py:53-63) is what limits the reference's candidate rate.
+// A line that Python would reject (not exactly two fields, an empty or non-integer id, a bad float) gets
+// h_ok = 0 and, like there, is skipped by the caller; so does a set with more than max_m ids.
+extern "C" int swga_parse_set_lines(const char *text, uint64_t n_bytes, uint32_t max_m, uint64_t cap,
+                                    int32_t *h_ids, double *h_weight, uint8_t *h_ok, uint64_t *n_lines,
+                                    uint64_t *consumed)
+{
+    ARG_CHECK((text || n_bytes == 0) && h_ids && h_weight && h_ok && n_lines && consumed && max_m > 0);
+    uint64_t pos = 0, line = 0;
+    while (pos < n_bytes && line < cap) {
+        const char *nl = static_cast<const char *>(memchr(text + pos, '\n', n_bytes - pos));
+        if (!nl) break;                                        // incomplete last line: left for the next block
+        const uint64_t end = (uint64_t)(nl - text);
+        int32_t *ids = h_ids + line * max_m;
+        for (uint32_t j = 0; j < max_m; ++j) ids[j] = -1;
+        bool ok = true;
+        uint64_t p = pos;
+        uint32_t m = 0;
+        // ids: decimal integers separated by ','; Python's int() also takes a sign and surrounding blanks, which
+        // set_finder never prints: anything but [+-]digits is a parse failure here as it is a ValueError there
+        for (;;) {
+            uint64_t q = p;
+            bool neg = false;
+            if (q < end && (text[q] == '+' || text[q] == '-')) { neg = text[q] == '-'; ++q; }
+            if (q >= end || text[q] < '0' || text[q] > '9') { ok = false; break; }
+            long long v = 0;
+            while (q < end && text[q] >= '0' && text[q] <= '9') {
+                v = v * 10 + (text[q] - '0');
+                if (v > 2147483647ll) { ok = false; break; }
+                ++q;
+            }
+            if (!ok) break;
+            if (neg && v != 0) { ok = false; break; }              // no vertex has a negative id (-1 is the padding)
+            if (m < max_m) ids[m] = (int32_t)v;
+            ++m;
+            p = q;
+            if (p < end && text[p] == ',') { ++p; continue; }
+            break;
+        }
+        if (ok && (p >= end || text[p] != ' ')) ok = false;    // exactly one ' ' between the two fields
+        double w = 0.0;
+        if (ok) {
+            ++p;
+            char tmp[64];
+            const uint64_t len = end - p;
+            if (len == 0 || len >= sizeof(tmp) || memchr(text + p, ' ', len)) {
+                ok = false;
+            } else {
+                memcpy(tmp, text + p, len);
+                tmp[len] = 0;
+                char *e = nullptr;
+                w = strtod(tmp, &e);
+                if (e == tmp || *e != 0) ok = false;
+            }
+        }
+        if (m > max_m) ok = false;
+        h_weight[line] = w;
+        h_ok[line] = ok ? 1 : 0;
+        ++line;
+        pos = end + 1;
+    }
+    *n_lines = line;
+    *consumed = pos;
+    return SWGA_OK;
+}

@@ -223,17 +223,76 @@ def find_sets(primers, gindex, bg_length, min_bg_bind_dist, max_fg_bind_dist, mi
         max_sets = float("inf")
     ordered = assign_ids(primers) if any(p._id is None for p in primers) else sorted(primers, key=lambda p: p._id)
     own_gen = lines is None
-    if own_gen:
-        build_graph(ordered, max_dimer_bp, graph_fp)
-        _message("Finding sets. If nothing appears, try relaxing your parameters.")
-        lines = sets.find(min_bg_bind_dist=min_bg_bind_dist, min_size=min_size, max_size=max_size,
-                          bg_length=bg_length, graph_fp=graph_fp, workers=workers)
     sl = score.SiteLists.from_index(gindex, [p.seq for p in ordered])
     index_of_id = {p._id: i for i, p in enumerate(ordered)}
     default_expr = score_expression.strip() == score.DEFAULT_EXPRESSION
     out = []
     passed = processed = 0
     smallest_max_dist = float("inf")
+
+    def emit(res, j, ids, bg):
+        variables = score._variables(res, j, len(ids), bg)
+        sc = float(res.score[j]) if default_expr else score.evaluate_expression(score_expression, variables)
+        out.append(dict(variables, _id=passed, primer_ids=ids, primers=[ordered[index_of_id[i]].seq for i in ids],
+                        score=sc, scoring_fn=score_expression))
+
+    if own_gen and workers <= 1:
+        # ---- block path: raw stdout blocks -> native parser -> one scoring launch per block ----
+        build_graph(ordered, max_dimer_bp, graph_fp)
+        _message("Finding sets. If nothing appears, try relaxing your parameters.")
+        max_m = max(max_size, 1)
+        lut = np.full(max(index_of_id) + 2, -1, dtype=np.int32)               # set_finder vertex id -> primer index
+        for i, k in index_of_id.items():
+            lut[i] = k
+        blocks = sets.find_blocks(min_bg_bind_dist=min_bg_bind_dist, min_size=min_size, max_size=max_size,
+                                  bg_length=bg_length, graph_fp=graph_fp)
+        carry = b""
+        try:
+            done = False
+            for chunk in blocks:
+                buf = carry + chunk
+                ids, weight, ok, consumed = score.parse_set_lines(buf, max_m)
+                carry = buf[consumed:]
+                if len(ids) == 0:
+                    continue
+                in_range = (ids >= -1) & (ids < len(lut))
+                idx = np.where(ids >= 0, lut[np.clip(ids, 0, len(lut) - 1)], -1)
+                ok &= in_range.all(axis=1) & ((idx >= 0) == (ids >= 0)).all(axis=1)
+                if not ok.all():
+                    text = buf[:consumed].split(b"\n")
+                    for li in np.nonzero(~ok)[0]:
+                        score.warn("Could not parse line:\n\t" + text[int(li)].decode("ascii", "replace"))
+                sel = np.nonzero(ok)[0]
+                if len(sel) == 0:
+                    continue
+                res = score.score_sets(sl, idx[sel], weight[sel], max_fg_bind_dist)
+                md = res.fg_max_dist
+                for j in np.nonzero(res.passed)[0]:
+                    j = int(j)
+                    passed += 1
+                    row_ids = [int(x) for x in ids[sel[j]] if x >= 0]
+                    emit(res, j, row_ids, float(weight[sel[j]]))
+                    if passed >= max_sets:
+                        processed += j + 1
+                        smallest_max_dist = min(smallest_max_dist, int(md[:j + 1].min()))
+                        _message("\nDone (scored %i sets)" % passed)
+                        done = True
+                        break
+                if done:
+                    break
+                processed += len(sel)
+                smallest_max_dist = min(smallest_max_dist, int(md.min()))
+                if on_status:
+                    on_status(processed, passed, smallest_max_dist)
+        finally:
+            blocks.close()
+        return out
+
+    if own_gen:
+        build_graph(ordered, max_dimer_bp, graph_fp)
+        _message("Finding sets. If nothing appears, try relaxing your parameters.")
+        lines = sets.find(min_bg_bind_dist=min_bg_bind_dist, min_size=min_size, max_size=max_size,
+                          bg_length=bg_length, graph_fp=graph_fp, workers=workers)
     it = iter(lines)
     n_take = 64
     try:
@@ -256,11 +315,7 @@ def find_sets(primers, gindex, bg_length, min_bg_bind_dist, max_fg_bind_dist, mi
                     on_status(processed, passed, smallest_max_dist)
                 if res.passed[j]:
                     passed += 1
-                    variables = score._variables(res, j, len(ids), bg)
-                    sc = float(res.score[j]) if default_expr else score.evaluate_expression(score_expression, variables)
-                    row = dict(variables, _id=passed, primer_ids=ids, primers=[ordered[index_of_id[i]].seq for i in ids],
-                               score=sc, scoring_fn=score_expression)
-                    out.append(row)
+                    emit(res, j, ids, bg)
                     if passed >= max_sets:
                         _message("\nDone (scored %i sets)" % passed)
                         done = True

@@ -37,6 +37,23 @@ def read_set_finder_line(line):
     return [int(_) for _ in primer_set.split(",")], float(weight)
 
 
+def parse_set_lines(block, max_m, cap=None):
+    """Every complete line of a block of set_finder output at once (native; what read_set_finder_line does per
+    line).  Returns (ids int32 [n][max_m] -1 padded, weight float64 [n], ok bool [n], consumed bytes)."""
+    lib = _lib.load()
+    if isinstance(block, str):
+        block = block.encode("ascii", "replace")
+    cap = block.count(b"\n") if cap is None else cap
+    ids = np.empty((max(cap, 1), max_m), dtype=np.int32)
+    w = np.empty(max(cap, 1), dtype=np.float64)
+    ok = np.zeros(max(cap, 1), dtype=np.uint8)
+    n_lines, consumed = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _lib.check(lib.swga_parse_set_lines(block, len(block), max_m, cap, _lib.ptr(ids), _lib.ptr(w), _lib.ptr(ok),
+                                        ctypes.byref(n_lines), ctypes.byref(consumed)))
+    n = n_lines.value
+    return ids[:n], w[:n], ok[:n].astype(bool), consumed.value
+
+
 def calculate_bg_dist_mean(primers, bg_length):
     """float(bg_length) / sum(bg_freq), or inf with a warning when nothing binds the background."""
     total_bg_freq = sum(p.bg_freq for p in primers)

@@ -62,6 +62,28 @@ def _find_sets(min_bg_bind_dist, bg_length, min_size, max_size, graph_fp, vertex
         process.wait()
 
 
+def find_blocks(min_bg_bind_dist, bg_length, min_size, max_size, graph_fp, vertex_ordering="weighted-coloring",
+                block_bytes=1 << 20):
+    """The same set_finder stream as `find(workers=1)`, handed over in raw blocks of stdout (bytes, not aligned
+    to lines) for score.parse_set_lines: no per-line Python between cliquer and the scoring kernel."""
+    cmd = [set_finder(), "-q", "-q", "--bg_freq", str(min_bg_bind_dist), "--bg_len", str(bg_length),
+           "--min", str(min_size), "--max", str(max_size), "--unweighted", "--all",
+           "--reorder", vertex_ordering, str(graph_fp)]
+    process = subprocess.Popen(cmd, stdout=subprocess.PIPE, preexec_fn=os.setsid, bufsize=0)
+    try:
+        while True:
+            chunk = process.stdout.read(block_bytes)
+            if not chunk:
+                break
+            yield chunk
+    finally:
+        time.sleep(0.1)
+        if process.poll() is None:
+            os.killpg(process.pid, signal.SIGKILL)
+        process.stdout.close()
+        process.wait()
+
+
 def _mp_find_sets(workers, **kwargs):
     procs = [_find_sets(vertex_ordering="random", **kwargs) for _ in range(workers)]
     try:

@@ -57,3 +57,30 @@ def test_read_set_finder_line_kat():
     assert score.read_set_finder_line("1,2,3 1.5") == ([1, 2, 3], 1.5)   # swga/tests/test_score.py:4-7
     with pytest.raises(ValueError):
         score.read_set_finder_line("not a line")
+
+
+def test_native_set_line_parser_equals_read_set_finder_line():
+    """swga_parse_set_lines against score.read_set_finder_line (swga/score.py:16-24) on well-formed lines (the
+    %f format of set_finder.c:442) and on every malformation Python rejects with ValueError."""
+    import numpy as np
+    rng = np.random.RandomState(5)
+    lines = []
+    for _ in range(2000):
+        m = int(rng.randint(1, 8))
+        ids = rng.randint(1, 5000, m)
+        lines.append(",".join(str(int(i)) for i in ids) + " %f" % rng.uniform(0, 1e7))
+    bad = ["", "1,2", "1,2 ", " 1.0", "1,,2 3.0", "1,2 3.0 4", "a,b 1.0", "1,2 x", "1;2 1.0", "1,2  1.0", "3, 4 1.0"]
+    lines[100:100] = bad
+    block = ("\n".join(lines) + "\n7,8 1.25").encode()                    # the last line is incomplete
+    ids, w, ok, consumed = score.parse_set_lines(block, 7)
+    assert consumed == len(block) - len("7,8 1.25") and len(ids) == len(lines)
+    for i, line in enumerate(lines):
+        try:
+            want_ids, want_w = score.read_set_finder_line(line)
+        except ValueError:
+            assert not ok[i], line
+            continue
+        assert ok[i], line
+        assert [int(x) for x in ids[i] if x >= 0] == want_ids and w[i] == want_w
+    ids2, w2, ok2, c2 = score.parse_set_lines(b"1,2,3,4 1.0\n", 3)          # more ids than max_m: flagged
+    assert not ok2[0] and c2 == 12
