@@ -526,9 +526,9 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     if (!ok) return SWGA_OK;
     const uint32_t nb = 1u << pb;
     const TableOffs offs = swga_make_offs(kmin, kmax);
-    // sample: one warp-tile (32 groups = 1024 starts) out of every `stride`, at least ~2^15 groups
+    // sample: one warp-tile (32 groups = 1024 starts) out of every `stride` (<= 64), at least ~2^15 groups
     const uint64_t n_groups = (n_starts + 31) / 32;
-    const uint32_t stride = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, n_groups >> 15));
+    const uint32_t stride = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, n_groups >> 15));
     const uint64_t n_sampled = (n_groups / (32ull * stride)) * 32 + std::min<uint64_t>(32, n_groups % (32ull * stride));
     const uint32_t ratio = (uint32_t)((n_groups + n_sampled - 1) / n_sampled);
     // upper bound of the layout (sum of estimate + slack over the buckets; Cauchy-Schwarz on the sqrt terms)

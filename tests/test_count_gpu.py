@@ -187,7 +187,7 @@ def test_partitioned_kernel_equals_direct_and_oracle(kmin, kmax, oracle, torch_c
 @pytest.mark.parametrize("mode_b", [False, True])
 def test_partitioned_kernel_on_hostile_composition(mode_b, oracle, torch_cuda):
     """The partitioned path sizes its buckets and its per-tile staging ranges from a strided SAMPLE of the
-    genome (one 1024-start block in every 16 Ki).  This genome is built to make the sample wrong in every
+    genome (one 1024-start block in every `stride`, stride <= 64).  This genome is built to make the sample wrong in every
     way the kernel has an exit for: composition that changes along the genome (staging ranges overflow
     into the per-tile list), a long two-base repeat (the list overflows too), poly-A / N runs (uniform
     groups; N -> G in mode B), and a repeat placed only where the sample does not look (global buckets
@@ -203,7 +203,8 @@ def test_partitioned_kernel_on_hostile_composition(mode_b, oracle, torch_cuda):
     seq[9_000_000:9_150_000] = ord("N")
     unit = np.frombuffer(b"ACGTTGCAAGGCTT" * 1200, dtype=np.uint8)
     pos = np.arange(16_000_000, 23_000_000)
-    hidden = pos[(pos % 16384) >= 1100]                        # never inside a sampled block
+    stride = min(64, max(1, ((n + 31) // 32) >> 15))           # the sampler's stride for this size (count_part.cu)
+    hidden = pos[(pos % (1024 * stride)) >= 1100]              # never inside a sampled block
     seq[hidden] = unit[hidden % len(unit)]
     rs = np.array([0, 7_999_999, 8_000_000, 8_000_010, n], dtype=np.uint64)
     d = torch.from_numpy(seq).cuda()
