@@ -162,6 +162,19 @@ int   swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint64_t n,
                              int kmin, int kmax, uint64_t n_starts, uint32_t *d_fwd);
 void *swga_ctx_compute_stream(swga_ctx *ctx);
 
+/* The same two calls fed with the FASTA FILE IMAGE (the bytes of `genome_fp`, e.g. a read-only mapping) --
+ * the closest equivalent of `dsk <genome_fp> <k>` (swga/kmers.py:44-47; Bank.cpp:150-209 record rules as in
+ * swga_fasta_scan).  No host copy of the joined bases is made: host threads parse line-aligned ranges of the
+ * image straight into pinned staging blocks, chunk by chunk, while the previous chunk is copied and counted.
+ * mode: 0 = A (split at 'N'), 1 = B (raw), -1 = DSK's own choice (swga_dsk_mode); the mode used, the number
+ * of bases and of records are returned through the last three pointers (each may be NULL).
+ * swga_count_fasta_stream accumulates the additive form into the caller-zeroed d_fwd on the context's compute
+ * stream and returns without synchronising it; swga_count_fasta_host returns the canonical tables in h_canon. */
+int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *h_file, uint64_t n_file, int mode, int kmin, int kmax,
+                            uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used);
+int swga_count_fasta_host(swga_ctx *ctx, const uint8_t *h_file, uint64_t n_file, int mode, int kmin, int kmax,
+                          uint32_t *h_canon, uint64_t *n_bases, uint64_t *n_rec, int *mode_used);
+
 /* The count -> primer-row merge of `swga count` (swga/commands/count.py:98-135) over the canonical
  * tables of the foreground, the background and (optionally, may be NULL) the exclusion sequences:
  * a k-mer survives when fg >= max(1, min_fg_bind), bg <= max_bg_bind (negative = no limit), its

@@ -55,6 +55,10 @@ SIGNATURES = {
     "swga_count_stream_host": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_vp]),
     "swga_ctx_compute_stream": (c_vp, [c_ctx]),
+    "swga_count_fasta_stream": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               c_vp, c_u64p, c_u64p, ctypes.POINTER(ctypes.c_int)]),
+    "swga_count_fasta_host": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             c_vp, c_u64p, c_u64p, ctypes.POINTER(ctypes.c_int)]),
     "swga_filter_primers": (ctypes.c_int, [c_ctx, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                            ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, c_vp, ctypes.c_uint32,
                                            c_vp, c_vp]),

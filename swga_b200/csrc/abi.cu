@@ -5,6 +5,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -192,7 +194,8 @@ struct ScanRange {
     uint64_t bad_pos = 0;
 };
 
-static void scan_range(const uint8_t *f, ScanRange &r, uint8_t *h_seq, uint64_t *h_rec_starts, uint64_t *h_hdr)
+static void scan_range(const uint8_t *f, ScanRange &r, uint8_t *h_seq, uint64_t *h_rec_starts, uint64_t *h_hdr,
+                       std::vector<uint64_t> *rec_local = nullptr)
 {
     const bool fill = h_seq != nullptr || h_rec_starts != nullptr;
     uint64_t total = r.base0, rec = r.rec0, rec_len = r.rec_len_in, pos = r.pos;
@@ -201,6 +204,7 @@ static void scan_range(const uint8_t *f, ScanRange &r, uint8_t *h_seq, uint64_t 
         const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + pos, '\n', r.end - pos));
         const uint64_t eol = nl ? (uint64_t)(nl - f) : r.end;  // index of '\n' or the end of the range (= end of file)
         if (is_rec_start(c)) {
+            if (rec_local) rec_local->push_back(total - r.base0);  // record start, in bases from the start of the range
             if (fill && h_rec_starts) h_rec_starts[rec] = total;
             if (fill && h_hdr) {
                 h_hdr[2 * rec] = pos + 1;
@@ -233,6 +237,40 @@ static void scan_range(const uint8_t *f, ScanRange &r, uint8_t *h_seq, uint64_t 
     r.recs = rec - r.rec0;
 }
 
+// Cuts the image into n_rg ranges of whole lines (cut t = the first line start at or after t * n / n_rg) and finds,
+// for each, whether the record it continues is still empty: walk back over the lines before the cut -- empty
+// lines do not count, a header line means "empty", any other line means "not empty".
+static void cut_ranges(const uint8_t *f, uint64_t n, unsigned n_rg, std::vector<ScanRange> &rg)
+{
+    rg.assign(n_rg, ScanRange());
+    std::vector<uint64_t> cut(n_rg + 1, n);
+    cut[0] = 0;
+    for (unsigned t = 1; t < n_rg; ++t) {
+        uint64_t p = std::max(cut[t - 1], n / n_rg * t);
+        if (p > 0 && p < n && f[p - 1] != '\n') {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + p, '\n', n - p));
+            p = nl ? (uint64_t)(nl - f) + 1 : n;
+        }
+        cut[t] = std::min(p, n);
+    }
+    for (unsigned t = 0; t < n_rg; ++t) {
+        rg[t].pos = cut[t];
+        rg[t].end = cut[t + 1];
+        uint64_t q = cut[t];
+        rg[t].rec_len_in = 0;
+        while (q > 0) {
+            uint64_t e = q - 1;                                // the '\n' that ends the previous line
+            uint64_t s0 = e;
+            while (s0 > 0 && f[s0 - 1] != '\n') --s0;          // start of that line
+            if (e > s0) {                                      // non-empty line
+                rg[t].rec_len_in = is_rec_start(f[s0]) ? 0 : 2;
+                break;
+            }
+            q = s0;
+        }
+    }
+}
+
 // Both passes (sizes, then fill) run on up to 16 host threads: the image is cut at line starts into ranges that
 // are scanned independently (a line never depends on another one except through "is the record still empty",
 // which a range recovers by looking at the lines before its start), then prefix sums place every range.
@@ -249,36 +287,8 @@ extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uin
     const char *env_chunk = getenv("SWGA_FASTA_CHUNK");          // bytes per range at least (tests force small ranges)
     const uint64_t per_thread_min = env_chunk && atoll(env_chunk) > 0 ? (uint64_t)atoll(env_chunk) : (8ull << 20);
     const unsigned n_thr = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(hw ? hw : 1, 16u), n / per_thread_min));
-    std::vector<ScanRange> rg(n_thr);
-    // cut points: the first line start at or after i * n / n_thr
-    std::vector<uint64_t> cut(n_thr + 1, n);
-    cut[0] = 0;
-    for (unsigned t = 1; t < n_thr; ++t) {
-        uint64_t p = std::max(cut[t - 1], n / n_thr * t);
-        if (p > 0 && p < n && f[p - 1] != '\n') {
-            const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + p, '\n', n - p));
-            p = nl ? (uint64_t)(nl - f) + 1 : n;
-        }
-        cut[t] = std::min(p, n);
-    }
-    for (unsigned t = 0; t < n_thr; ++t) {
-        rg[t].pos = cut[t];
-        rg[t].end = cut[t + 1];
-        // is the record that this range continues still empty?  walk back over the lines before the cut:
-        // empty lines do not count, a header line means "empty", any other line means "not empty"
-        uint64_t q = cut[t];
-        rg[t].rec_len_in = 0;
-        while (q > 0) {
-            uint64_t e = q - 1;                                // the '\n' that ends the previous line
-            uint64_t s0 = e;
-            while (s0 > 0 && f[s0 - 1] != '\n') --s0;          // start of that line
-            if (e > s0) {                                      // non-empty line
-                rg[t].rec_len_in = is_rec_start(f[s0]) ? 0 : 2;
-                break;
-            }
-            q = s0;
-        }
-    }
+    std::vector<ScanRange> rg;
+    cut_ranges(f, n, n_thr, rg);
     auto run = [&](uint8_t *seq, uint64_t *rs, uint64_t *hdr) {
         if (n_thr == 1) {
             scan_range(f, rg[0], seq, rs, hdr);
@@ -358,6 +368,45 @@ extern "C" int swga_count_genome_device(swga_ctx *ctx, const uint8_t *d_ascii, u
     return SWGA_OK;
 }
 
+// One chunk of the host pipelines: H2D of `len` bases from pinned memory into staging buffer b (stream s_copy),
+// then pack, record marks and the count of the chunk's first `owned` start positions (stream s_comp).  `origin`
+// is the genome coordinate of the chunk's first base.
+static int enqueue_chunk(swga_ctx *ctx, int b, const uint8_t *src, uint64_t len, uint64_t origin, uint64_t owned,
+                         const uint64_t *h_rec_starts, uint64_t n_rec, int mask_mode, int kmin, int kmax, uint32_t *d_fwd)
+{
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));   // the kernels that last read this buffer
+    CUDA_TRY(cudaMemcpyAsync(ctx->ascii[b].p, src, len, cudaMemcpyHostToDevice, ctx->s_copy));
+    CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
+    uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
+    TRY(swga_pack(ctx, (const uint8_t *)ctx->ascii[b].p, len, mask_mode, packed, brk, ctx->s_comp));
+    if (n_rec > 1) {
+        // records whose start s satisfies origin < s <= origin + len
+        const uint64_t *lo = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, origin);
+        const uint64_t *hi = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, origin + len);
+        if (hi > lo)
+            TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p + (lo - h_rec_starts), (uint64_t)(hi - lo),
+                                         origin, len, brk, ctx->s_comp));
+    }
+    TRY(swga_count_accumulate(ctx, packed, brk, owned, kmin, kmax, d_fwd, ctx->s_comp));
+    CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
+    return SWGA_OK;
+}
+
+static int ensure_stage(swga_ctx *ctx, size_t want)
+{
+    if (ctx->h_stage_cap >= want) return SWGA_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));              // no copy may still be reading the old blocks
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_stage[i]) CUDA_TRY(cudaFreeHost(ctx->h_stage[i]));
+        ctx->h_stage[i] = nullptr;
+        ctx->h_stage_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&ctx->h_stage[i], want, cudaHostAllocDefault));
+    }
+    ctx->h_stage_cap = want;
+    return SWGA_OK;
+}
+
 // ---- whole-genome counting, host buffers (what swga/kmers.py would call instead of `dsk`) -----
 // The genome is cut into chunks of CHUNK start positions; chunk i needs bases
 // [a_i, min(n, b_i + kmax - 1)).  H2D of chunk i+1 (stream s_copy) overlaps pack + count of chunk i
@@ -395,17 +444,7 @@ extern "C" int swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
         if (e != cudaSuccess) cudaGetLastError();
         pinned = (e == cudaSuccess && attr.type == cudaMemoryTypeHost);
     }
-    if (!pinned && n > 0) {
-        const size_t want = (size_t)cap + 64;
-        if (ctx->h_stage_cap < want) {
-            for (int i = 0; i < 2; ++i) {
-                if (ctx->h_stage[i]) CUDA_TRY(cudaFreeHost(ctx->h_stage[i]));
-                ctx->h_stage[i] = nullptr;
-                CUDA_TRY(cudaHostAlloc(&ctx->h_stage[i], want, cudaHostAllocDefault));
-            }
-            ctx->h_stage_cap = want;
-        }
-    }
+    if (!pinned && n > 0) TRY(ensure_stage(ctx, (size_t)cap + 64));
     int it = 0;
     for (uint64_t a = 0; a < n_starts; a += CHUNK, ++it) {
         const int b = it & 1;
@@ -430,23 +469,50 @@ extern "C" int swga_count_stream_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
             }
             src = dst;
         }
-        if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));
-        CUDA_TRY(cudaMemcpyAsync(ctx->ascii[b].p, src, len, cudaMemcpyHostToDevice, ctx->s_copy));
-        CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
-        uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
-        TRY(swga_pack(ctx, (const uint8_t *)ctx->ascii[b].p, len, mask_mode, packed, brk, ctx->s_comp));
-        if (n_rec > 1) {
-            // records whose start s satisfies a < s <= a + len
-            const uint64_t *lo = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, a);
-            const uint64_t *hi = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, a + len);
-            if (hi > lo)
-                TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p + (lo - h_rec_starts),
-                                             (uint64_t)(hi - lo), a, len, brk, ctx->s_comp));
-        }
-        TRY(swga_count_accumulate(ctx, packed, brk, e_starts - a, kmin, kmax, d_fwd, ctx->s_comp));
-        CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
+        TRY(enqueue_chunk(ctx, b, src, len, a, e_starts - a, h_rec_starts, n_rec, mask_mode, kmin, kmax, d_fwd));
     }
+    return SWGA_OK;
+}
+
+// Result tables to the caller's buffer at the end of the *_host calls (on s_comp, synchronised on return).  A
+// pageable destination (a plain numpy array) would be a driver-staged copy with the page faults of a fresh
+// buffer inside it (~3 GB/s measured): it goes through the pinned staging blocks instead, 16 MiB at a time,
+// copied out by a few host threads while the next block is on the bus.
+static int d2h_result(swga_ctx *ctx, void *h_dst, const void *d_src, size_t bytes)
+{
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, h_dst);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (e == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->s_comp));
+        CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+        return SWGA_OK;
+    }
+    const size_t BLK = 16u << 20;
+    TRY(ensure_stage(ctx, BLK));
+    const size_t n_blk = (bytes + BLK - 1) / BLK;
+    auto issue = [&](size_t i) -> int {
+        const size_t off = i * BLK, len = std::min(BLK, bytes - off);
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_stage[i & 1], (const uint8_t *)d_src + off, len, cudaMemcpyDeviceToHost, ctx->s_comp));
+        CUDA_TRY(cudaEventRecord(ctx->ev_done[i & 1], ctx->s_comp));
+        return SWGA_OK;
+    };
+    if (n_blk) TRY(issue(0));
+    for (size_t i = 0; i < n_blk; ++i) {
+        if (i + 1 < n_blk) TRY(issue(i + 1));
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_done[i & 1]));
+        const size_t off = i * BLK, len = std::min(BLK, bytes - off);
+        const uint8_t *src = (const uint8_t *)ctx->h_stage[i & 1];
+        uint8_t *dst = (uint8_t *)h_dst + off;
+        const size_t per = (len + 3) / 4;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < 4; ++t) {
+            const size_t lo = std::min(len, t * per), hi = std::min(len, lo + per);
+            if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+        }
+        for (auto &x : th) x.join();
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
     return SWGA_OK;
 }
 
@@ -469,8 +535,165 @@ extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
     TRY(swga_count_stream_host(ctx, h_seq, n, h_rec_starts, n_rec, mode_b, kmin, kmax, n, fwd));
     TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
     TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
-    CUDA_TRY(cudaMemcpyAsync(h_canon, canon, words * 4, cudaMemcpyDeviceToHost, ctx->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+    TRY(d2h_result(ctx, h_canon, canon, words * 4));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    return SWGA_OK;
+}
+
+// ---- whole-genome counting straight from a FASTA file image -----------------------------------------
+// What `dsk <genome.fasta> <k>` is to swga/kmers.py:44-47, for all k at once and without a host copy of the
+// joined bases: the image is cut into ranges of whole lines (~4 MiB); a first pass over all ranges (host
+// threads) finds the bases and records of each, which gives the record boundaries and DSK's read mode; the
+// second pass parses the ranges of one chunk (<= 64 Mi bases) DIRECTLY into a pinned staging block while the
+// previous chunk is on the bus and the one before is being counted.  A chunk owns the starts of all its bases
+// but the last kmax-1, which it hands to the next chunk as the head of that chunk's block.
+template <class F>
+static void parallel_for(unsigned n_items, unsigned n_thr, F fn)
+{
+    if (n_thr <= 1 || n_items <= 1) {
+        for (unsigned i = 0; i < n_items; ++i) fn(i);
+        return;
+    }
+    std::atomic<unsigned> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < std::min(n_thr, n_items); ++t)
+        th.emplace_back([&] {
+            for (;;) {
+                const unsigned i = next.fetch_add(1);
+                if (i >= n_items) break;
+                fn(i);
+            }
+        });
+    for (auto &x : th) x.join();
+}
+
+static uint64_t env_u64(const char *name, uint64_t dflt)
+{
+    const char *v = getenv(name);
+    return v && atoll(v) > 0 ? (uint64_t)atoll(v) : dflt;
+}
+
+extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
+                                       uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used)
+{
+    ARG_CHECK(ctx && (f || n_file == 0) && d_fwd && mode >= -1 && mode <= 1);
+    if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
+        swga_set_error("need 2 <= kmin <= kmax <= %d", SWGA_KMAX_LIMIT);
+        return SWGA_E_ARG;
+    }
+    if (n_file > 0 && f[0] != '>' && f[0] != '@') {
+        swga_set_error("not a FASTA image: first byte is 0x%02x, expected '>' (DSK would read it as a list of file names)",
+                       f[0]);
+        return SWGA_E_FORMAT;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned n_thr = std::min<unsigned>(hw ? hw : 1, 16u);
+    const uint64_t range_bytes = env_u64("SWGA_FASTA_CHUNK", 4ull << 20);       // tests force small ranges and chunks
+    const uint64_t CHUNK = std::max<uint64_t>(64, env_u64("SWGA_STREAM_CHUNK", 64ull << 20));
+    const unsigned n_rg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_file / range_bytes, 1u << 20));
+    const bool trace = getenv("SWGA_TRACE") != nullptr;       // host-side stage times on stderr
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_fill = 0, t_wait = 0, t_enq = 0;
+    const double t0 = now();
+    std::vector<ScanRange> rg;
+    cut_ranges(f, n_file, n_rg, rg);
+    // pass 1: bases and records of every range
+    std::vector<std::vector<uint64_t>> rec_local(n_rg);
+    parallel_for(n_rg, n_thr, [&](unsigned i) { scan_range(f, rg[i], nullptr, nullptr, nullptr, &rec_local[i]); });
+    uint64_t total = 0, max_bases = 0;
+    std::vector<uint64_t> rs;
+    for (unsigned i = 0; i < n_rg; ++i) {
+        if (rg[i].status != SWGA_OK) {
+            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
+                           (unsigned long long)rg[i].bad_pos);
+            return SWGA_E_FORMAT;
+        }
+        rg[i].base0 = total;
+        for (uint64_t l : rec_local[i]) rs.push_back(total + l);
+        total += rg[i].bases;
+        max_bases = std::max(max_bases, rg[i].bases);
+    }
+    const uint64_t nr = rs.size();
+    rs.push_back(total);
+    const double t1 = now();
+    if (mode < 0) mode = swga_dsk_mode(rs.data(), nr);
+    if (n_bases) *n_bases = total;
+    if (n_rec) *n_rec = nr;
+    if (mode_used) *mode_used = mode;
+    if (total == 0) return SWGA_OK;
+    const int mask_mode = mode ? SWGA_MASK_NONE : SWGA_MASK_N;
+    const uint64_t halo = (uint64_t)kmax - 1;
+    const uint64_t cap = std::max(CHUNK, max_bases) + halo;    // a block holds the carried halo + at least one range
+    for (int i = 0; i < 2; ++i) {
+        TRY(swga_ensure(ctx, ctx->ascii[i], cap + 64));
+        TRY(swga_ensure(ctx, ctx->packed2[i], swga_packed_words(cap) * 4));
+        TRY(swga_ensure(ctx, ctx->brk2[i], swga_brk_words(cap) * 4));
+    }
+    TRY(ensure_stage(ctx, (size_t)cap + 64));
+    TRY(swga_ensure(ctx, ctx->recs, (nr + 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, rs.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));              // `rs` is pageable: it must not go away under the copy
+    // pass 2: chunks of whole ranges
+    uint64_t origin = 0, carry = 0, prev_len = 0;              // genome coordinate of the block's first base; carried bases
+    int it = 0, prev_b = 0;
+    for (unsigned r = 0; r < n_rg; ++it) {
+        const int b = it & 1;
+        unsigned r1 = r + 1;
+        uint64_t fresh = rg[r].bases;
+        while (r1 < n_rg && fresh + rg[r1].bases <= CHUNK) fresh += rg[r1++].bases;
+        const double ta = now();
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_h2d[b]));         // the copy that last read this block
+        const double tb = now();
+        uint8_t *blk = (uint8_t *)ctx->h_stage[b];
+        if (carry) memcpy(blk, (const uint8_t *)ctx->h_stage[prev_b] + (prev_len - carry), carry);
+        const uint64_t a0 = rg[r].base0;
+        parallel_for(r1 - r, n_thr, [&](unsigned j) {
+            ScanRange x = rg[r + j];
+            x.base0 = carry + (x.base0 - a0);                  // where this range's bases go inside the block
+            x.rec0 = 0;
+            scan_range(f, x, blk, nullptr, nullptr);
+        });
+        const double tc = now();
+        const uint64_t len = carry + fresh;
+        const bool last = r1 == n_rg;
+        const uint64_t owned = last ? len : (len > halo ? len - halo : 0);
+        if (owned > 0)
+            TRY(enqueue_chunk(ctx, b, blk, len, origin, owned, rs.data(), nr, mask_mode, kmin, kmax, d_fwd));
+        t_wait += tb - ta;
+        t_fill += tc - tb;
+        t_enq += now() - tc;
+        origin += owned;
+        carry = len - owned;
+        prev_len = len;
+        prev_b = b;
+        r = r1;
+    }
+    if (trace)
+        fprintf(stderr, "[swga_count_fasta_stream] %u ranges, %d chunks: pass 1 %.1f ms, setup %.1f ms, fill %.1f ms, "
+                        "waiting for blocks %.1f ms, enqueue %.1f ms\n", n_rg, it, (t1 - t0) * 1e3,
+                (now() - t1) * 1e3 - (t_fill + t_wait + t_enq) * 1e3, t_fill * 1e3, t_wait * 1e3, t_enq * 1e3);
+    return SWGA_OK;
+}
+
+extern "C" int swga_count_fasta_host(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
+                                     uint32_t *h_canon, uint64_t *n_bases, uint64_t *n_rec, int *mode_used)
+{
+    ARG_CHECK(ctx && h_canon);
+    if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
+        swga_set_error("need 2 <= kmin <= kmax <= %d", SWGA_KMAX_LIMIT);
+        return SWGA_E_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const uint64_t words = swga_tables_words(kmin, kmax);
+    TRY(swga_ensure(ctx, ctx->fwd, words * 4));
+    TRY(swga_ensure(ctx, ctx->canon, words * 4));
+    uint32_t *fwd = (uint32_t *)ctx->fwd.p, *canon = (uint32_t *)ctx->canon.p;
+    CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
+    TRY(swga_count_fasta_stream(ctx, f, n_file, mode, kmin, kmax, fwd, n_bases, n_rec, mode_used));
+    TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
+    TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
+    TRY(d2h_result(ctx, h_canon, canon, words * 4));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
     return SWGA_OK;
 }

@@ -71,17 +71,20 @@ def parse_fasta_bytes(data, path=None, pin=False):
     return Genome(seq, rs, names, path)
 
 
-def read_fasta(path, pin=False):
-    """Read a FASTA file, plain or gzip-compressed (DSK opens its input through zlib's gzopen, which reads
-    both: ext/dsk/minia/Bank.cpp:39,275)."""
+def read_image(path):
+    """The bytes of a FASTA file, plain or gzip-compressed (DSK opens its input through zlib's gzopen, which
+    reads both: ext/dsk/minia/Bank.cpp:39,275), as a uint8 array."""
     with open(path, "rb") as f:
         magic = f.read(2)
     if magic == b"\x1f\x8b":
         import gzip
         with gzip.open(path, "rb") as f:
-            data = np.frombuffer(f.read(), dtype=np.uint8)
-    elif os.path.getsize(path) > 0:
-        data = np.memmap(path, dtype=np.uint8, mode="r")          # the reader's threads read the page cache directly
-    else:
-        data = np.zeros(0, dtype=np.uint8)
-    return parse_fasta_bytes(data, path=os.path.abspath(path), pin=pin)
+            return np.frombuffer(f.read(), dtype=np.uint8)
+    if os.path.getsize(path) > 0:
+        return np.memmap(path, dtype=np.uint8, mode="r")          # the reader's threads read the page cache directly
+    return np.zeros(0, dtype=np.uint8)
+
+
+def read_fasta(path, pin=False):
+    """Read a FASTA file into a Genome (joined bases on the host)."""
+    return parse_fasta_bytes(read_image(path), path=os.path.abspath(path), pin=pin)

@@ -82,13 +82,22 @@ class CountTables(object):
 
 def count_all(genome, kmin=DEFAULT_KMIN, kmax=DEFAULT_KMAX, device=None):
     """Count every canonical k-mer, k in [kmin, kmax], of a FASTA file (path) or `fasta.Genome`
-    through the host-buffer C-ABI call.  Returns CountTables on the host (numpy)."""
+    through the host-buffer C-ABI calls.  Returns CountTables on the host (numpy).  A path goes through
+    swga_count_fasta_host: the file image is parsed straight into the library's pinned staging blocks, no host
+    copy of the joined bases is made (`n_bases`, `n_records`, `mode_b` of the file are set on the result)."""
+    import ctypes
     lib = _lib.load()
     ctx = _lib.context(device)
-    if not isinstance(genome, fasta.Genome):
-        genome = fasta.read_fasta(genome, pin=False)        # pageable: the library stages it (see swga_count_stream_host)
     words = int(lib.swga_tables_words(kmin, kmax))
     out = np.empty(words, dtype=np.uint32)
+    if not isinstance(genome, fasta.Genome):
+        image = fasta.read_image(genome)
+        nb, nr, mode = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_int(0)
+        _lib.check(lib.swga_count_fasta_host(ctx.h, _lib.ptr(image) if len(image) else None, len(image), -1, kmin, kmax,
+                                             _lib.ptr(out), ctypes.byref(nb), ctypes.byref(nr), ctypes.byref(mode)))
+        tables = CountTables(out, kmin, kmax)
+        tables.n_bases, tables.n_records, tables.mode_b = nb.value, nr.value, bool(mode.value)
+        return tables
     rs = np.ascontiguousarray(genome.rec_starts, dtype=np.uint64)
     _lib.check(lib.swga_count_genome_host(ctx.h, _lib.ptr(genome.seq) if genome.n_bases else None,
                                           genome.n_bases, _lib.ptr(rs), genome.n_records,

@@ -41,8 +41,9 @@ def count_tables_device(genome, kmin, kmax, device=None):
     host buffer in chunks (H2D overlapped with pack + count; a pageable buffer goes through the library's pinned
     staging blocks, which is cheaper than pinning a genome-sized buffer for one pass)."""
     import torch
+    image = None
     if not isinstance(genome, fasta.Genome):
-        genome = fasta.read_fasta(genome, pin=False)
+        image = fasta.read_image(genome)                    # a path: parsed chunk by chunk inside the library
     lib = _lib.load()
     ctx = _lib.context(device)
     dev = torch.device("cuda", ctx.device)
@@ -52,7 +53,12 @@ def count_tables_device(genome, kmin, kmax, device=None):
         with torch.cuda.stream(cs):
             fwd = torch.zeros(words, dtype=torch.int32, device=dev)
             canon = torch.zeros(words, dtype=torch.int32, device=dev)
-            if genome.n_bases:
+            if image is not None:
+                _lib.check(lib.swga_count_fasta_stream(ctx.h, _lib.ptr(image) if len(image) else None, len(image), -1,
+                                                       kmin, kmax, _lib.ptr(fwd), None, None, None))
+                _lib.check(lib.swga_count_finalize(ctx.h, kmin, kmax, _lib.ptr(fwd), cs.cuda_stream))
+                _lib.check(lib.swga_fold_canonical(ctx.h, kmin, kmax, _lib.ptr(fwd), _lib.ptr(canon), cs.cuda_stream))
+            elif genome.n_bases:
                 rs = np.ascontiguousarray(genome.rec_starts, dtype=np.uint64)
                 _lib.check(lib.swga_count_stream_host(ctx.h, _lib.ptr(genome.seq), genome.n_bases, _lib.ptr(rs),
                                                       genome.n_records, int(genome.dsk_mode_b), kmin, kmax,

@@ -224,3 +224,80 @@ def test_partitioned_kernel_on_hostile_composition(mode_b, oracle, torch_cuda):
     assert np.array_equal(out[1], out[2])
     want = oracle.count_dense_allk(seq, rs, 5, 12, mode_b=int(mode_b))
     assert np.array_equal(out[2], want)
+
+
+def _file_tables(path, kmin, kmax):
+    from swga_b200 import kmers
+    return kmers.count_all(str(path), kmin, kmax)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_file_image_call_matches_real_dsk(case, oracle, dsk_golden, torch_cuda, tmp_path):
+    """swga_count_fasta_host (FASTA file image in, canonical tables out) on the golden cases: same tables as the
+    host-buffer call, the oracle and the real dsk; DSK's read mode is chosen inside the library."""
+    from swga_b200 import fasta
+    data = golden_case_bytes(case)
+    fp = tmp_path / "g.fa"
+    fp.write_bytes(data)
+    seq, rs = oracle.fasta_parse_dsk(data)
+    kmin, kmax = (3, 12) if case == "edge_a" else (5, 12)
+    tabs = _file_tables(fp, kmin, kmax)
+    g = fasta.parse_fasta_bytes(data)
+    assert (tabs.n_bases, tabs.n_records, tabs.mode_b) == (len(seq), len(rs) - 1, g.dsk_mode_b)
+    for k in range(kmin, kmax + 1):
+        got = tabs.table(k)
+        assert np.array_equal(got, oracle.count_dense(seq, rs, k)), (case, k)
+        gold = dsk_golden[case].get(str(k))
+        if gold:
+            assert table_digest(got, k) == (gold["distinct"], gold["sum"], gold["md5"])
+
+
+def test_file_image_chunking(oracle, torch_cuda, tmp_path, monkeypatch):
+    """Ranges of a few bytes and chunks of a few dozen bases: every chunk hands its last kmax-1 bases to the next
+    one, records / 'N' runs / CRLF / empty lines fall on range and chunk boundaries, some chunks are shorter
+    than the halo.  Also the degenerate images."""
+    from swga_b200 import fasta, kmers
+    rng = np.random.RandomState(5)
+    pieces = [b">h\n", b">h x y\n", b"\n", b"\r\n", b"ACGT\n", b"ACGTNNAC\r\n", b"A\n", b"\r", b"acgtRYK\n",
+              b"G" * 300 + b"\n", b"TTTT", b">\n", b"ACGTTGCATGCAAGTC" * 9 + b"\n", b"N" * 40 + b"\n"]
+    images = [b"", b">only\n", b">x\nACG\n", b">x\nACGTA", b">a\nAC\n>b\nGT\n>c\nACGTAC\n"]
+    for it in range(12):
+        images.append(b">first\n" + b"".join(pieces[i] for i in rng.randint(0, len(pieces), int(rng.randint(5, 120)))))
+    for chunk, stream in (("1", "64"), ("7", "100"), ("64", "1000")):
+        monkeypatch.setenv("SWGA_FASTA_CHUNK", chunk)
+        monkeypatch.setenv("SWGA_STREAM_CHUNK", stream)
+        for i, data in enumerate(images):
+            fp = tmp_path / "c.fa"
+            fp.write_bytes(data)
+            seq, rs = oracle.fasta_parse_dsk(data)
+            for mode_b in (0, 1):
+                import ctypes
+                from swga_b200 import _lib
+                lib, ctx = _lib.load(), _lib.context(0)
+                image = np.frombuffer(data, dtype=np.uint8)
+                out = np.empty(int(lib.swga_tables_words(4, 9)), dtype=np.uint32)
+                nb = ctypes.c_uint64(0)
+                _lib.check(lib.swga_count_fasta_host(ctx.h, _lib.ptr(image) if len(image) else None, len(image), mode_b,
+                                                     4, 9, _lib.ptr(out), ctypes.byref(nb), None, None))
+                assert nb.value == len(seq)
+                want = oracle.count_dense_allk(seq, rs, 4, 9, mode_b=mode_b)
+                assert np.array_equal(out, want), (chunk, stream, i, mode_b, data[:60])
+
+
+def test_file_image_large_multi_chunk(oracle, torch_cuda, tmp_path):
+    """Default range / chunk sizes on a file of several chunks (200 Mbp, 5 records, mode B): equal to the
+    host-buffer call on the parsed genome (which the partitioned-kernel tests tie to the oracle)."""
+    from swga_b200 import fasta, kmers, synth
+    n = 200_000_000
+    seq = synth.bases(77, 0, n, 0.41)
+    seq[50_000_000:50_003_000] = ord("N")
+    rs = np.array([0, 1_500_000, 70_000_000, 70_000_005, 140_000_011, n], dtype=np.uint64)
+    fp = str(tmp_path / "big.fa")
+    synth.write_fasta(fp, seq, rs)
+    a = kmers.count_all(fp, 5, 12)
+    g = fasta.read_fasta(fp)
+    assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs)
+    b = kmers.count_all(g, 5, 12)
+    assert (a.n_bases, a.n_records, a.mode_b) == (n, 5, True)
+    assert np.array_equal(a.block, b.block)
+    assert int(a.table(12).astype(np.int64).sum()) > 0

@@ -15,6 +15,9 @@ for it in range(2):
     tabs = kmers.count_all(g, 5, 12); torch.cuda.synchronize(); t3 = time.perf_counter()
     g2 = fasta.parse_fasta_bytes(raw, pin=False); t4 = time.perf_counter()
     tabs = kmers.count_all(g2, 5, 12); torch.cuda.synchronize(); t5 = time.perf_counter()
+    t6 = time.perf_counter(); tabs2 = kmers.count_all(path, 5, 12); t7 = time.perf_counter()
+    assert np.array_equal(tabs.block, tabs2.block)
+    print("   file image -> tables (swga_count_fasta_host): %.3fs -> %.2f Gbases/s" % (t7 - t6, n / (t7 - t6) / 1e9), flush=True)
     tp = time.perf_counter(); x = torch.empty(n, dtype=torch.uint8, pin_memory=True); tq = time.perf_counter()
     print("   pageable (library staging): parse %.3fs count %.3fs ; pinned alloc alone %.3fs" % (t4 - t3, t5 - t4, tq - tp), flush=True); del x
     print("read %.3fs  parse %.3fs (%.2f GB/s)  count(host buffers) %.3fs  total %.3fs -> %.2f Gbases/s"
