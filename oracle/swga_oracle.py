@@ -340,3 +340,51 @@ def score_set(primer_locations, max_fg_bind_dist, bg_dist_mean, chr_ends,
     set_score, variables = default_score_set(expression, primer_locations, binding_locations,
                                              max_dist, bg_dist_mean)
     return set_score, variables, max_dist
+
+
+# --------------------------------------------------------------------------- exports (cold path)
+
+def lorenz(distances):
+    """swga/stats.py:57-81."""
+    distances.sort()
+    height = 0
+    lz = []
+    for dist in distances:
+        height += dist
+        lz.append(height)
+    _max = float(max(lz))
+    return [l / _max for l in lz]
+
+
+def bedgraph_hits_per_record(primer_locations, chr_ends, window_size, step_size=None):
+    """BedGraph._hits_per_record, swga/export.py:91-133, loop for loop (Python-2 `/` on ints is `//`);
+    primer_locations = list of {record: [pos]}.  Returns [(record, midpoint, hits)]."""
+    from collections import Counter
+    window_size = int(window_size)
+    step_size = int(step_size) if step_size else window_size // 5
+    out = []
+    for record_name, ends in chr_ends.items():
+        record_length = ends[1] + 1
+        this_window_size = window_size
+        if this_window_size > record_length:
+            this_window_size = record_length
+        this_step_size = step_size
+        if this_step_size > this_window_size:
+            this_step_size = this_window_size
+        counter = Counter()
+        for locations in primer_locations:
+            counter.update(Counter(locations[record_name]))
+        for start in range(0, int(record_length - this_window_size), this_step_size):
+            end = start + this_window_size
+            midpoint = (end + start) // 2
+            hits = sum([counter[i] for i in range(start, end)])
+            out.append((record_name, midpoint, hits))
+    return out
+
+
+def py2_float_str(x):
+    """Python 2's str(float) (floatobject.c float_str: PyFloat_STR_PRECISION = 12, '.0' appended to integers)."""
+    s = "%.12g" % x
+    if "." not in s and "e" not in s and "n" not in s and "i" not in s:
+        s += ".0"
+    return s

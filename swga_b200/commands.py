@@ -1,4 +1,4 @@
-"""The `swga init | count | filter | find_sets | score` command surface over the workspace database
+"""The `swga init | count | filter | find_sets | score | export | activate | summary` command surface over the workspace database
 (swga/commands/*.py), with the data-parallel work done by the B200 kernels:
 
   init       commands/init.py:86-190      genome lengths -> _metadata, default binding-rate parameters
@@ -8,6 +8,9 @@
                                           and per-primer Gini (d) for the primers that reach that step
   find_sets  commands/find_sets.py:22-103 graph + host set_finder + batched scoring (d), rows into `set`
   score      commands/score.py:16-77      one user-supplied set, interactive (never rejected)
+  export     commands/export.py:36-165    primers / sets as TSV, Lorenz curve, BED files, bedgraph (swga_b200/export.py)
+  activate   commands/activate.py:6-18    locations for a list of primers (locate kernel), mark them active
+  summary    commands/summary.py:55-124   counts and the best set (plain text, no terminal colours)
 
 Option names and defaults are the reference's (`commands/specfiles/*.yaml`).  Prompts (`click.confirm`)
 become the `force` argument: without it a command that would delete rows raises instead of asking.
@@ -21,6 +24,7 @@ import argparse
 import os
 import sys
 
+from . import export as _export
 from . import fasta, kmers, locate, pipeline, score, workspace
 
 MIN_FG_RATE = 0.00001            # commands/init.py:34-38
@@ -275,6 +279,118 @@ def score_set(db_name=workspace.DEFAULT_DB_FNAME, input=None, primers=None, scor
         return dict(variables, score=sc, scoring_fn=score_expression, _id=set_id)
 
 
+# ---------------------------------------------------------------------------------------------- export / activate / summary
+
+def export(what="sets", db_name=workspace.DEFAULT_DB_FNAME, output=None, order_by=None, descending=False, limit=-1,
+           ids=None, no_header=False, opts_str=None, window_size=10000, step_size=None, output_folder=None):
+    """Export.run (commands/export.py:36-76).  `output`: a writable text file (default stdout)."""
+    ws, meta = _open(db_name)
+    out = output if output is not None else sys.stdout
+    limit = None if limit is None or limit < 0 else limit
+    with ws:
+        sel = dict(ids=ids, order_by=order_by, descending=descending, limit=limit)
+        if what in ("set", "sets"):
+            _export.export_rows(_export.SET_FIELDS, _export.select_rows(ws, "sets", **sel), out, not no_header)
+        if what in ("primer", "primers"):
+            _export.export_rows(_export.PRIMER_FIELDS, _export.select_rows(ws, "primers", **sel), out, not no_header)
+        if what == "lorenz" or "bed" in what:
+            sets_ = _export.select_rows(ws, "sets", **sel)
+            locs = {}
+            for st in sets_:
+                ps = {p.seq: p for p in ws.primers_by_seqs(st["primers"])}
+                locs[st["_id"]] = [(seq, ps[seq].locations) for seq in st["primers"]]
+            if what == "lorenz":
+                chr_ends = locate.chromosome_ends(meta["fg_file"])
+                _export.export_lorenz([(i, [l for _, l in pl]) for i, pl in locs.items()], out, chr_ends, not no_header)
+            outpath = output_folder if output_folder else os.getcwd()
+            if what == "bedfile":
+                for i, pl in locs.items():
+                    message("Exporting set {} and its primers as bedfiles...".format(i))
+                    _export.write_bedfiles(i, pl, meta["fg_file"], outpath)
+            elif what == "bedgraph":
+                chr_ends = locate.chromosome_ends(meta["fg_file"])
+                for i, pl in locs.items():
+                    message("Exporting set {} as bedgraph...".format(i))
+                    _export.write_bedgraph(i, [l for _, l in pl], meta["fg_file"], chr_ends, outpath, opts_str,
+                                           window_size, step_size)
+
+
+def activate(input, db_name=workspace.DEFAULT_DB_FNAME, reset=False, tm_fn=None, gindex=None):
+    """Activate.run (commands/activate.py:6-18): fill in melting temperatures (when a `tm_fn` is supplied: the
+    reference's comes from the third-party `melt`) and binding locations of the listed primers, mark them active.
+    `reset` is accepted and, as in the reference, not used."""
+    ws, meta = _open(db_name)
+    with ws:
+        with open(input) as f:
+            seqs = kmers.parse_kmer_file(f)
+        ps = ws.primers_by_seqs(seqs)
+        have = set(p.seq for p in ps)
+        for s_ in seqs:
+            if s_ not in have:
+                message(s_ + " not in the database; skipping. Add it manually with `swga count --input <file>` ")
+        if tm_fn is not None:
+            todo = [p for p in ps if p.tm is None]
+            for p in todo:
+                p.tm = tm_fn(p.seq)
+            ws.update_primers(todo, fields=("tm",))
+        todo = [p for p in ps if p.locations is None]
+        if todo:
+            message("Finding binding locations for {} primers...".format(len(todo)))
+            gindex = gindex or locate.genome_index(meta["fg_file"])
+            pipeline.update_locations(todo, gindex)
+            ws.update_primers(todo, fields=("_locations",))
+        for p in ps:
+            p.active = True
+        ws.update_primers(ps, fields=("active",))
+        message("Marked {} primers as active.".format(len(ps)))
+        if len(ps) < 1:
+            message("Note: Fewer than 1 primers were selected ({} passed all the filters). You may want to try less "
+                    "restrictive filtering parameters.".format(len(ps)))
+        return [p.seq for p in ps]
+
+
+def summary(db_name=workspace.DEFAULT_DB_FNAME, out=None):
+    """Summary.run (commands/summary.py:55-124) as a dict; the text is written to `out` (default stdout)."""
+    ws, meta = _open(db_name)
+    with ws:
+        avg_fg, avg_bg, nprimers = ws.db.execute('SELECT AVG("fg_freq"), AVG("bg_freq"), COUNT("seq") FROM "primer"').fetchone()
+        avg_fg, avg_bg = (0, 0) if avg_fg is None or avg_bg is None else (avg_fg, avg_bg)
+        nactive = ws.db.execute('SELECT COUNT(*) FROM "primer" WHERE "active" = 1').fetchone()[0]
+        min_tm, max_tm, avg_tm = ws.db.execute('SELECT MIN("tm"), MAX("tm"), AVG("tm") FROM "primer" WHERE "active" = 1').fetchone()
+        nsets = ws.count_sets()
+        best = ws.sets('"score"')[0] if nsets > 0 else None
+    info = dict(fg_genome_fp=meta["fg_file"], bg_genome_fp=meta["bg_file"], exclude_fp=meta["ex_file"], nprimers=nprimers,
+                nactive=nactive, avg_fg_bind=avg_fg, avg_bg_bind=avg_bg, fg_bind_ratio=avg_fg / float(meta["fg_length"]),
+                bg_bind_ratio=avg_bg / float(meta["bg_length"]), min_tm=min_tm, max_tm=max_tm, avg_tm=avg_tm, nsets=nsets,
+                best_set=best)
+    lines = ["swga_b200 (workspace v{})".format(meta["version"]), "---------------",
+             "  Foreground genome:\n    {fg_genome_fp}\n  Background genome:\n    {bg_genome_fp}\n"
+             "  Excluded sequences:\n    {exclude_fp}".format(**info), "", "PRIMER SUMMARY", "---------------",
+             "There are {} primers in the database. {}".format(nprimers, "Run `swga count` to find possible primers."
+                                                               if nprimers == 0 else ""),
+             "{} are marked as active. {}".format(nactive, "Run `swga filter` to identify primers to use."
+                                                  if nactive == 0 else ""),
+             "The average number of foreground genome binding sites is {avg_fg_bind:.0f}.\n"
+             "    (avg binding / genome_length = {fg_bind_ratio:05f})".format(**info),
+             "The average number of background genome binding sites is {avg_bg_bind:.0f}.\n"
+             "    (avg binding / genome_length = {bg_bind_ratio:05f})".format(**info),
+             ("The melting temp of the primers ranges between {min_tm:.2f}C and {max_tm:.2f}C with an average of "
+              "{avg_tm:.2f}C.".format(**info) if nactive > 0 and min_tm and max_tm else
+              "No melting temps have been calculated yet."), "", "SETS SUMMARY", "---------------",
+             "There are {} sets in the database.".format(nsets)]
+    if best is not None:
+        lines += ["The best scoring set is #{}, with {} primers and a score of {:03f}.".format(
+                      best["_id"], best["set_size"], best["score"]),
+                  "Various statistics:"] + \
+                 [" - {key:.<16}: {val: >10s}".format(key=k, val=best[k] if isinstance(best[k], str) else "{:,G}".format(best[k]))
+                  for k in _export.SET_FIELDS if k not in ("_id", "pids", "score", "primers")] + \
+                 ["The primers in Set {} are:".format(best["_id"]), ", ".join(best["primers"])]
+    else:
+        lines.append("Run `swga find_sets` after identifying valid primers to begin collecting sets.")
+    (out if out is not None else sys.stdout).write("\n".join(lines) + "\n")
+    return info
+
+
 # ---------------------------------------------------------------------------------------------- CLI
 
 def main(argv=None):
@@ -307,12 +423,30 @@ def main(argv=None):
     p.add_argument("--input", required=True)
     p.add_argument("--score_expression")
     p.add_argument("--force", action="store_true")
+    p = sub.add_parser("export")
+    p.add_argument("what", nargs="?", default="sets",
+                   choices=["set", "sets", "primer", "primers", "bedfile", "bedgraph", "lorenz"])
+    p.add_argument("--output", type=argparse.FileType("w"))
+    p.add_argument("--order_by")
+    p.add_argument("--descending", action="store_true")
+    p.add_argument("--limit", type=int)
+    p.add_argument("--ids", type=int, nargs="*")
+    p.add_argument("--no_header", action="store_true")
+    p.add_argument("--opts_str")
+    p.add_argument("--window_size", type=float)
+    p.add_argument("--step_size", type=int)
+    p.add_argument("--output_folder")
+    p = sub.add_parser("activate")
+    p.add_argument("input")
+    p.add_argument("--reset", action="store_true")
+    sub.add_parser("summary")
     args, _unknown = ap.parse_known_args(argv)                  # unknown options are tolerated (_command.py:48)
     kw = {k: v for k, v in vars(args).items() if k not in ("cmd", "db") and v is not None and v is not False}
     if args.cmd == "init":
         init(args.fg_genome_fp, args.bg_genome_fp, args.exclude_fp, db_name=args.db, force=args.force)
     else:
-        fn = {"count": count, "filter": filter, "find_sets": find_sets, "score": score_set}[args.cmd]
+        fn = {"count": count, "filter": filter, "find_sets": find_sets, "score": score_set, "export": export,
+              "activate": activate, "summary": summary}[args.cmd]
         fn(db_name=args.db, **kw)
     return 0
 

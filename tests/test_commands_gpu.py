@@ -1,4 +1,4 @@
-"""`init -> count -> filter -> find_sets -> score` through swga_b200.commands on a workspace database,
+"""`init -> count -> filter -> find_sets -> score -> export / summary / activate` through swga_b200.commands on a workspace database,
 compared with the oracle restatement of the reference's commands (swga/commands/*.py)."""
 import os
 
@@ -105,6 +105,39 @@ def test_commands_end_to_end(ws_dir, oracle):
     assert out["_id"] == -1 and out["fg_max_dist"] == md and out["score"] == pytest.approx(sc, rel=1e-12)
     out2 = commands.score_set(db_name=db, primers=[by_id[4].seq, by_id[5].seq], force=True)
     assert out2["_id"] == -2
+
+    # ---- export (sets table, Lorenz curve, bedgraph, BED files), summary, activate
+    import io
+    from swga_b200 import export
+    buf = io.StringIO()
+    commands.export("sets", db_name=db, output=buf, order_by="score", limit=3)
+    lines = buf.getvalue().splitlines()
+    assert lines[0].split("\t") == list(export.SET_FIELDS) and len(lines) == 1 + min(3, len(sets_db) + 2)
+    first = sets_db[0]
+    locs1 = [next(p for p in by_id.values() if p.seq == s).locations for s in first["primers"]]
+    buf = io.StringIO()
+    commands.export("lorenz", db_name=db, output=buf, ids=[first["_id"]])
+    curve = oracle.lorenz(oracle.seq_diff(oracle.linearize_binding_sites(locs1, ends)))
+    assert buf.getvalue() == "SetID\tCDF\n%d\t%s\n" % (first["_id"], ",".join(oracle.py2_float_str(v) for v in curve))
+    outdir = str(ws_dir / "exports")
+    commands.export("bedgraph", db_name=db, ids=[first["_id"]], output_folder=outdir, window_size=5000.0, opts_str="x=1")
+    bg_lines = open(os.path.join(outdir, "fg_export", "set_%d" % first["_id"], "set_%d.bedgraph" % first["_id"])).read().splitlines()
+    want_rows = oracle.bedgraph_hits_per_record(locs1, ends, 5000)
+    assert bg_lines[0] == "track type=bedGraph x=1" and bg_lines[1:] == ["%s %d %d %d" % (r[0], r[1], r[1], r[2]) for r in want_rows]
+    assert sum(r[2] for r in want_rows) > 0
+    commands.export("bedfile", db_name=db, ids=[first["_id"]], output_folder=outdir)
+    whole = open(os.path.join(outdir, "fg_export", "set_%d" % first["_id"], "whole_set.bed")).read().splitlines()
+    assert len(whole) == 1 + sum(len(v) for l in locs1 for v in l.values())
+    info = commands.summary(db_name=db, out=io.StringIO())
+    assert info["nsets"] == len(sets_db) + 2 and info["nactive"] == len(by_id) and info["best_set"]["_id"] is not None
+    with workspace.connection(db) as ws:
+        idle = [p.seq for p in ws.primers('"active" = 0 AND "_locations" IS NULL')[:2]]
+    lst = ws_dir / "activate.txt"
+    lst.write_text("\n".join(idle + ["ACGTACGTAC"]) + "\n")                 # the last one is not in the database
+    assert sorted(commands.activate(str(lst), db_name=db)) == sorted(idle)
+    with workspace.connection(db) as ws:
+        for p in ws.primers_by_seqs(idle):
+            assert p.active and p.locations == oracle.binding_sites(p.seq, recs)
 
 
 def test_count_input_adds_listed_primers_like_the_reference(ws_dir, oracle, tmp_path):
