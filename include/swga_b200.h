@@ -175,6 +175,15 @@ int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *h_file, uint64_t n_fil
 int swga_count_fasta_host(swga_ctx *ctx, const uint8_t *h_file, uint64_t n_file, int mode, int kmin, int kmax,
                           uint32_t *h_canon, uint64_t *n_bases, uint64_t *n_rec, int *mode_used);
 
+/* The heterodimer compatibility graph of `swga find_sets`: graph.build_edges (swga/graph.py:7-17) with
+ * kmers.max_sequential_nt (swga/kmers.py:59-91) for all pairs at once.  d_seqs holds n primers as upper-case
+ * ACGT ASCII rows of `stride` bytes, d_len their lengths (<= max_len <= 256).  Row i of the bit matrix d_adj
+ * (words_per_row >= ceil(n/32) words per row, every word of the first ceil(n/32) is written) gets bit (j & 31) of
+ * word (j >> 5) set when i < j and the pair is compatible: neither sequence contains the other and their
+ * longest complementary run is <= max_binding.  Set bits read row by row = itertools.combinations order. */
+int swga_build_edges(swga_ctx *ctx, const uint8_t *d_seqs, uint32_t n, uint32_t stride, const uint32_t *d_len,
+                     uint32_t max_len, int max_binding, uint32_t *d_adj, uint32_t words_per_row, void *stream);
+
 /* The count -> primer-row merge of `swga count` (swga/commands/count.py:98-135) over the canonical
  * tables of the foreground, the background and (optionally, may be NULL) the exclusion sequences:
  * a k-mer survives when fg >= max(1, min_fg_bind), bg <= max_bg_bind (negative = no limit), its

@@ -62,6 +62,8 @@ SIGNATURES = {
     "swga_filter_primers": (ctypes.c_int, [c_ctx, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                            ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, c_vp, ctypes.c_uint32,
                                            c_vp, c_vp]),
+    "swga_build_edges": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, ctypes.c_uint32, ctypes.c_int,
+                                        c_vp, ctypes.c_uint32, c_vp]),
     "swga_parse_set_lines": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, c_vp, c_vp,
                                             c_vp, c_u64p, c_u64p]),
     "swga_write_dsk_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, c_vp, ctypes.c_uint32, c_u64p]),

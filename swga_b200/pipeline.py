@@ -171,8 +171,9 @@ def assign_ids(primers):
     return ordered
 
 
-def build_edges(primers, max_binding):
-    """graph.py:7-17: heterodimer-compatible pairs (neither contains the other)."""
+def build_edges_host(primers, max_binding):
+    """graph.py:7-17 as the reference writes it (a Python double loop per pair): the statement of what
+    `build_edges` computes, kept for the known-answer tests; not used by the commands."""
     edges = []
     for p1, p2 in itertools.combinations(primers, 2):
         if (p1.seq not in p2.seq) and (p2.seq not in p1.seq):
@@ -181,10 +182,43 @@ def build_edges(primers, max_binding):
     return edges
 
 
-def build_graph(primers, max_hetdimer_bind, outfile):
+def build_edges(primers, max_binding, device=None):
+    """graph.py:7-17: heterodimer-compatible pairs (neither contains the other, longest complementary run
+    <= max_binding), in itertools.combinations order -- all pairs in one launch (swga_build_edges)."""
+    import torch
+    primers = list(primers)
+    n = len(primers)
+    if n < 2:
+        return []
+    seqs = [p.seq for p in primers]
+    for s in seqs:
+        if set(s) - set("ACGT"):
+            raise KeyError("primer %r: max_sequential_nt knows A, C, G, T only (swga/kmers.py:64-70)" % s)
+    lens = np.asarray([len(s) for s in seqs], dtype=np.uint32)
+    stride = (int(lens.max()) + 15) // 16 * 16
+    rows = np.zeros((n, stride), dtype=np.uint8)
+    for i, s in enumerate(seqs):
+        rows[i, :len(s)] = np.frombuffer(s.encode("ascii"), dtype=np.uint8)
+    lib = _lib.load()
+    ctx = _lib.context(device)
+    dev = torch.device("cuda", ctx.device)
+    wpr = (n + 31) // 32
+    with torch.cuda.device(dev):
+        d_rows, d_len = torch.from_numpy(rows).to(dev), torch.from_numpy(lens.view(np.int32)).to(dev)
+        d_adj = torch.zeros(n * wpr, dtype=torch.int32, device=dev)
+        _lib.check(lib.swga_build_edges(ctx.h, _lib.ptr(d_rows), n, stride, _lib.ptr(d_len), int(lens.max()),
+                                        int(max_binding), _lib.ptr(d_adj), wpr, torch.cuda.current_stream().cuda_stream))
+        adj = d_adj.cpu().numpy()
+    bits = np.unpackbits(adj.view(np.uint8).reshape(n, wpr * 4), axis=1, bitorder="little")[:, :n]
+    ii, jj = np.nonzero(bits)
+    ids = [p._id for p in primers]
+    return [[ids[i], ids[j]] for i, j in zip(ii.tolist(), jj.tolist())]
+
+
+def build_graph(primers, max_hetdimer_bind, outfile, edges_fn=None):
     """graph.py:20-60: DIMACS graph, vertex weight = bg_freq or 1."""
     primers = assign_ids(primers)
-    edges = build_edges(primers, max_hetdimer_bind)
+    edges = (edges_fn or build_edges)(primers, max_hetdimer_bind)
     if not edges:
         raise ValueError("No compatible primers. Try relaxing your parameters.")
     with open(outfile, "w") as out:

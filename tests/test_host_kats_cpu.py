@@ -18,18 +18,19 @@ def P(_id, seq, **kw):
 
 
 def test_reference_graph_kats():
+    """The host statement of build_edges; tests/test_graph_gpu.py runs the same answers through the kernel."""
     ref = P(0, "ATGCTC")
     for seq in ("CAGCAT", "GAGGTA", "ATCGAG"):                           # heterodimers: no edge
-        assert pipeline.build_edges([ref, P(1, seq)], 2) == []
-    assert pipeline.build_edges([ref, P(4, "TTCCAC")], 2) == [[0, 4]]    # valid pair
-    assert pipeline.build_edges([ref, P(5, "ATGC")], 2) == []            # subsequence
+        assert pipeline.build_edges_host([ref, P(1, seq)], 2) == []
+    assert pipeline.build_edges_host([ref, P(4, "TTCCAC")], 2) == [[0, 4]]    # valid pair
+    assert pipeline.build_edges_host([ref, P(5, "ATGC")], 2) == []            # subsequence
 
 
 def test_reference_build_graph_kat(tmp_path):
     primers = [P(None, "ATGC", fg_freq=1, bg_freq=2, ratio=1.0), P(None, "GGCC", fg_freq=1, bg_freq=3, ratio=0.5),
                P(None, "CCTA", fg_freq=2, bg_freq=0, ratio=float("inf"))]
     out = tmp_path / "graph"
-    pipeline.build_graph(primers, 3, str(out))
+    pipeline.build_graph(primers, 3, str(out), edges_fn=pipeline.build_edges_host)
     # ids by ratio descending (primers.py:255-268); vertex weight = bg_freq or 1 (graph.py:45-52)
     assert out.read_text() == "p sp 3 3\nn 1 1\nn 2 2\nn 3 3\ne 1 2\ne 1 3\ne 2 3\n"
 
