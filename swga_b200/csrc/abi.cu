@@ -81,8 +81,10 @@ extern "C" void swga_ctx_destroy(swga_ctx *c)
     }
     for (int i = 0; i < 4; ++i)
         if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
         if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->h_recs[i]) cudaFreeHost(c->h_recs[i]);
+    }
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     delete c;
@@ -504,9 +506,10 @@ static int d2h_result(swga_ctx *ctx, void *h_dst, const void *d_src, size_t byte
         const size_t off = i * BLK, len = std::min(BLK, bytes - off);
         const uint8_t *src = (const uint8_t *)ctx->h_stage[i & 1];
         uint8_t *dst = (uint8_t *)h_dst + off;
-        const size_t per = (len + 3) / 4;
+        const unsigned n_cp = 8;                               // mostly page faults of a fresh destination: they scale with threads
+        const size_t per = ((len + n_cp - 1) / n_cp + 4095) & ~size_t(4095);
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < 4; ++t) {
+        for (unsigned t = 0; t < n_cp; ++t) {
             const size_t lo = std::min(len, t * per), hi = std::min(len, lo + per);
             if (hi > lo) th.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
         }
@@ -542,11 +545,11 @@ extern "C" int swga_count_genome_host(swga_ctx *ctx, const uint8_t *h_seq, uint6
 
 // ---- whole-genome counting straight from a FASTA file image -----------------------------------------
 // What `dsk <genome.fasta> <k>` is to swga/kmers.py:44-47, for all k at once and without a host copy of the
-// joined bases: the image is cut into ranges of whole lines (~4 MiB); a first pass over all ranges (host
-// threads) finds the bases and records of each, which gives the record boundaries and DSK's read mode; the
-// second pass parses the ranges of one chunk (<= 64 Mi bases) DIRECTLY into a pinned staging block while the
-// previous chunk is on the bus and the one before is being counted.  A chunk owns the starts of all its bases
-// but the last kmax-1, which it hands to the next chunk as the head of that chunk's block.
+// joined bases.  The image is cut into ranges of whole lines (~4 MiB).  DSK's read mode is decided from the head
+// of the file (decide_mode).  Then ONE pass: the ranges of a chunk (<= 64 MiB of file) are parsed by the host
+// threads DIRECTLY into a pinned staging block while the previous chunk is on the bus and the one before is being
+// counted.  A chunk owns the starts of all its bases but the last kmax-1, which the next chunk finds at the head
+// of its device buffer (a device-to-device copy of 11 bytes).
 template <class F>
 static void parallel_for(unsigned n_items, unsigned n_thr, F fn)
 {
@@ -573,6 +576,54 @@ static uint64_t env_u64(const char *name, uint64_t dflt)
     return v && atoll(v) > 0 ? (uint64_t)atoll(v) : dflt;
 }
 
+// DSK's read mode from the head of the file: ranges are sized batch by batch until one of the first 10,001
+// records is seen to exceed 1,000,000 bases (mode B), or 10,001 records have ended without one (mode A), or the
+// file ends.  For a chromosome-scale genome that is the first batch.
+static int decide_mode(const uint8_t *f, std::vector<ScanRange> &rg, unsigned n_thr, int *mode)
+{
+    const unsigned n_rg = (unsigned)rg.size();
+    uint64_t total = 0, n_seen = 0, last_start = 0;
+    bool big = false;
+    for (unsigned r0 = 0; r0 < n_rg; r0 += n_thr) {
+        const unsigned r1 = std::min(n_rg, r0 + n_thr);
+        std::vector<std::vector<uint64_t>> loc(r1 - r0);
+        parallel_for(r1 - r0, n_thr, [&](unsigned j) { scan_range(f, rg[r0 + j], nullptr, nullptr, nullptr, &loc[j]); });
+        for (unsigned j = 0; j < r1 - r0; ++j) {
+            if (rg[r0 + j].status != SWGA_OK) {
+                swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
+                               (unsigned long long)rg[r0 + j].bad_pos);
+                return SWGA_E_FORMAT;
+            }
+            for (uint64_t l : loc[j]) {
+                const uint64_t s = total + l;
+                if (n_seen >= 1 && n_seen <= 10001 && s - last_start > 1000000) big = true;   // record n_seen-1 has ended
+                last_start = s;
+                ++n_seen;
+            }
+            total += rg[r0 + j].bases;
+        }
+        if (n_seen >= 1 && n_seen <= 10001 && total - last_start > 1000000) big = true;       // the record still open
+        if (big || n_seen > 10001) break;
+    }
+    *mode = big ? 1 : 0;
+    return SWGA_OK;
+}
+
+static int ensure_recs(swga_ctx *ctx, size_t want)
+{
+    if (ctx->h_recs_cap >= want) return SWGA_OK;
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+    want = std::max<size_t>(want * 2, 1 << 16);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_recs[i]) CUDA_TRY(cudaFreeHost(ctx->h_recs[i]));
+        ctx->h_recs[i] = nullptr;
+        ctx->h_recs_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&ctx->h_recs[i], want, cudaHostAllocDefault));
+    }
+    ctx->h_recs_cap = want;
+    return SWGA_OK;
+}
+
 extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
                                        uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used)
 {
@@ -590,7 +641,7 @@ extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t
     const unsigned hw = std::thread::hardware_concurrency();
     const unsigned n_thr = std::min<unsigned>(hw ? hw : 1, 16u);
     const uint64_t range_bytes = env_u64("SWGA_FASTA_CHUNK", 4ull << 20);       // tests force small ranges and chunks
-    const uint64_t CHUNK = std::max<uint64_t>(64, env_u64("SWGA_STREAM_CHUNK", 64ull << 20));
+    const uint64_t CHUNK = std::max<uint64_t>(64, env_u64("SWGA_STREAM_CHUNK", 64ull << 20));   // file bytes per chunk
     const unsigned n_rg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_file / range_bytes, 1u << 20));
     const bool trace = getenv("SWGA_TRACE") != nullptr;       // host-side stage times on stderr
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -598,68 +649,100 @@ extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t
     const double t0 = now();
     std::vector<ScanRange> rg;
     cut_ranges(f, n_file, n_rg, rg);
-    // pass 1: bases and records of every range
-    std::vector<std::vector<uint64_t>> rec_local(n_rg);
-    parallel_for(n_rg, n_thr, [&](unsigned i) { scan_range(f, rg[i], nullptr, nullptr, nullptr, &rec_local[i]); });
-    uint64_t total = 0, max_bases = 0;
-    std::vector<uint64_t> rs;
-    for (unsigned i = 0; i < n_rg; ++i) {
-        if (rg[i].status != SWGA_OK) {
-            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
-                           (unsigned long long)rg[i].bad_pos);
-            return SWGA_E_FORMAT;
-        }
-        rg[i].base0 = total;
-        for (uint64_t l : rec_local[i]) rs.push_back(total + l);
-        total += rg[i].bases;
-        max_bases = std::max(max_bases, rg[i].bases);
-    }
-    const uint64_t nr = rs.size();
-    rs.push_back(total);
+    if (mode < 0) TRY(decide_mode(f, rg, n_thr, &mode));
     const double t1 = now();
-    if (mode < 0) mode = swga_dsk_mode(rs.data(), nr);
-    if (n_bases) *n_bases = total;
-    if (n_rec) *n_rec = nr;
     if (mode_used) *mode_used = mode;
-    if (total == 0) return SWGA_OK;
     const int mask_mode = mode ? SWGA_MASK_NONE : SWGA_MASK_N;
     const uint64_t halo = (uint64_t)kmax - 1;
-    const uint64_t cap = std::max(CHUNK, max_bases) + halo;    // a block holds the carried halo + at least one range
+    // chunks = runs of whole ranges of at most CHUNK file bytes (at least one range); the largest one sizes the blocks
+    uint64_t max_ext = 0;
+    for (unsigned r = 0; r < n_rg;) {
+        unsigned r1 = r + 1;
+        while (r1 < n_rg && rg[r1].end - rg[r].pos <= CHUNK) ++r1;
+        max_ext = std::max(max_ext, rg[r1 - 1].end - rg[r].pos);
+        r = r1;
+    }
+    if (max_ext > (2ull << 30)) {
+        swga_set_error("a line of the FASTA image is longer than 2 GiB: read it with swga_fasta_scan + swga_count_genome_host");
+        return SWGA_E_FORMAT;
+    }
+    const uint64_t cap = max_ext + halo;
     for (int i = 0; i < 2; ++i) {
         TRY(swga_ensure(ctx, ctx->ascii[i], cap + 64));
         TRY(swga_ensure(ctx, ctx->packed2[i], swga_packed_words(cap) * 4));
         TRY(swga_ensure(ctx, ctx->brk2[i], swga_brk_words(cap) * 4));
     }
-    TRY(ensure_stage(ctx, (size_t)cap + 64));
-    TRY(swga_ensure(ctx, ctx->recs, (nr + 1) * 8));
-    CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, rs.data(), (nr + 1) * 8, cudaMemcpyHostToDevice, ctx->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));              // `rs` is pageable: it must not go away under the copy
-    // pass 2: chunks of whole ranges
-    uint64_t origin = 0, carry = 0, prev_len = 0;              // genome coordinate of the block's first base; carried bases
+    TRY(ensure_stage(ctx, (size_t)max_ext + 64));
+    // ONE pass over the image: the ranges of a chunk are parsed by the host threads, each into the slot of the
+    // pinned block that mirrors its place in the file (a range never yields more bases than it has bytes), and go
+    // to the device with one copy per range, packed together behind the last kmax-1 bases of the previous chunk.
+    std::vector<std::vector<uint64_t>> rec_local(n_thr * 64);
+    std::vector<uint64_t> rs;                                  // record starts so far (genome coordinates)
+    uint64_t origin = 0, carry = 0, prev_len = 0, total = 0;   // origin: genome coordinate of the block's first base
     int it = 0, prev_b = 0;
     for (unsigned r = 0; r < n_rg; ++it) {
         const int b = it & 1;
         unsigned r1 = r + 1;
-        uint64_t fresh = rg[r].bases;
-        while (r1 < n_rg && fresh + rg[r1].bases <= CHUNK) fresh += rg[r1++].bases;
+        while (r1 < n_rg && rg[r1].end - rg[r].pos <= CHUNK) ++r1;
+        const unsigned cnt = r1 - r;
+        if (rec_local.size() < cnt) rec_local.resize(cnt);
         const double ta = now();
-        CUDA_TRY(cudaEventSynchronize(ctx->ev_h2d[b]));         // the copy that last read this block
+        CUDA_TRY(cudaEventSynchronize(ctx->ev_h2d[b]));         // the copies that last read this block
         const double tb = now();
         uint8_t *blk = (uint8_t *)ctx->h_stage[b];
-        if (carry) memcpy(blk, (const uint8_t *)ctx->h_stage[prev_b] + (prev_len - carry), carry);
-        const uint64_t a0 = rg[r].base0;
-        parallel_for(r1 - r, n_thr, [&](unsigned j) {
-            ScanRange x = rg[r + j];
-            x.base0 = carry + (x.base0 - a0);                  // where this range's bases go inside the block
+        const uint64_t f0 = rg[r].pos;
+        parallel_for(cnt, n_thr, [&](unsigned j) {
+            ScanRange &x = rg[r + j];
+            x.base0 = x.pos - f0;                              // slot of this range inside the block
             x.rec0 = 0;
-            scan_range(f, x, blk, nullptr, nullptr);
+            rec_local[j].clear();
+            scan_range(f, x, blk, nullptr, nullptr, &rec_local[j]);
         });
         const double tc = now();
+        // device layout of the chunk: [carry][range r][range r + 1] ...
+        uint8_t *dst = (uint8_t *)ctx->ascii[b].p;
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[b], 0));   // the kernels that last read this buffer
+        if (carry)
+            CUDA_TRY(cudaMemcpyAsync(dst, (const uint8_t *)ctx->ascii[prev_b].p + (prev_len - carry), carry,
+                                     cudaMemcpyDeviceToDevice, ctx->s_copy));
+        uint64_t fresh = 0;
+        for (unsigned j = 0; j < cnt; ++j) {
+            const ScanRange &x = rg[r + j];
+            if (x.status != SWGA_OK) {
+                swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
+                               (unsigned long long)x.bad_pos);
+                return SWGA_E_FORMAT;
+            }
+            for (uint64_t l : rec_local[j]) rs.push_back(total + fresh + l);
+            if (x.bases)
+                CUDA_TRY(cudaMemcpyAsync(dst + carry + fresh, blk + x.base0, x.bases, cudaMemcpyHostToDevice, ctx->s_copy));
+            fresh += x.bases;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
+        total += fresh;
         const uint64_t len = carry + fresh;
         const bool last = r1 == n_rg;
         const uint64_t owned = last ? len : (len > halo ? len - halo : 0);
-        if (owned > 0)
-            TRY(enqueue_chunk(ctx, b, blk, len, origin, owned, rs.data(), nr, mask_mode, kmin, kmax, d_fwd));
+        if (owned > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
+            uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
+            TRY(swga_pack(ctx, dst, len, mask_mode, packed, brk, ctx->s_comp));
+            // record boundaries inside the chunk: starts s with origin < s <= origin + len (the first record never marks)
+            const uint64_t *lo = std::upper_bound(rs.data(), rs.data() + rs.size(), origin);
+            const uint64_t *hi = std::upper_bound(rs.data(), rs.data() + rs.size(), origin + len);
+            if (hi > lo) {
+                const size_t bytes = (size_t)(hi - lo) * 8;
+                TRY(ensure_recs(ctx, bytes));
+                CUDA_TRY(cudaEventSynchronize(ctx->ev_done[b]));   // the copy that last read this pinned list
+                memcpy(ctx->h_recs[b], lo, bytes);
+                TRY(swga_ensure(ctx, ctx->recs, bytes));
+                CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, ctx->h_recs[b], bytes, cudaMemcpyHostToDevice, ctx->s_comp));
+                TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p, (uint64_t)(hi - lo), origin, len, brk,
+                                             ctx->s_comp));
+            }
+            TRY(swga_count_accumulate(ctx, packed, brk, owned, kmin, kmax, d_fwd, ctx->s_comp));
+            CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
+        }
         t_wait += tb - ta;
         t_fill += tc - tb;
         t_enq += now() - tc;
@@ -669,8 +752,10 @@ extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t
         prev_b = b;
         r = r1;
     }
+    if (n_bases) *n_bases = total;
+    if (n_rec) *n_rec = rs.size();
     if (trace)
-        fprintf(stderr, "[swga_count_fasta_stream] %u ranges, %d chunks: pass 1 %.1f ms, setup %.1f ms, fill %.1f ms, "
+        fprintf(stderr, "[swga_count_fasta_stream] %u ranges, %d chunks: mode %.1f ms, setup %.1f ms, parse %.1f ms, "
                         "waiting for blocks %.1f ms, enqueue %.1f ms\n", n_rg, it, (t1 - t0) * 1e3,
                 (now() - t1) * 1e3 - (t_fill + t_wait + t_enq) * 1e3, t_fill * 1e3, t_wait * 1e3, t_enq * 1e3);
     return SWGA_OK;
@@ -690,11 +775,20 @@ extern "C" int swga_count_fasta_host(swga_ctx *ctx, const uint8_t *f, uint64_t n
     TRY(swga_ensure(ctx, ctx->canon, words * 4));
     uint32_t *fwd = (uint32_t *)ctx->fwd.p, *canon = (uint32_t *)ctx->canon.p;
     CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
+    const bool trace = getenv("SWGA_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     TRY(swga_count_fasta_stream(ctx, f, n_file, mode, kmin, kmax, fwd, n_bases, n_rec, mode_used));
     TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
     TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
+    const double t1 = now();
+    if (trace) CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+    const double t2 = now();
     TRY(d2h_result(ctx, h_canon, canon, words * 4));
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    if (trace)
+        fprintf(stderr, "[swga_count_fasta_host] stream %.1f ms, device tail %.1f ms, result copy %.1f ms\n", (t1 - t0) * 1e3,
+                (t2 - t1) * 1e3, (now() - t2) * 1e3);
     return SWGA_OK;
 }
 

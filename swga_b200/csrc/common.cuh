@@ -50,6 +50,8 @@ struct swga_ctx {
     DevBuf packed, brk, ascii[2], packed2[2], brk2[2], fwd, canon, recs, scratch;
     void *h_stage[2] = {nullptr, nullptr};             // pinned staging for pageable host genomes (64 MiB each)
     size_t h_stage_cap = 0;
+    void *h_recs[2] = {nullptr, nullptr};              // pinned: record starts of the chunk in flight (file-image path)
+    size_t h_recs_cap = 0;
     DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp, bucket_data, bucket_meta;
     uint32_t score_sort_cap = 4096;                    // raw sites per set up to which k_score_sort is used (0 = never)
     unsigned long long *part_stats = nullptr;          // inside bucket_meta: exits taken by the last partitioned count

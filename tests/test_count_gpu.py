@@ -301,3 +301,25 @@ def test_file_image_large_multi_chunk(oracle, torch_cuda, tmp_path):
     assert (a.n_bases, a.n_records, a.mode_b) == (n, 5, True)
     assert np.array_equal(a.block, b.block)
     assert int(a.table(12).astype(np.int64).sum()) > 0
+
+
+def test_file_image_gzip_and_errors(oracle, torch_cuda, tmp_path):
+    """A gzip-compressed FASTA gives the same tables (DSK reads both through gzopen); a file that is not FASTA
+    and a FASTQ file are refused with the reader's messages."""
+    import gzip
+    from swga_b200 import _lib, kmers
+    data = golden_case_bytes("synth_mode_a")
+    (tmp_path / "p.fa").write_bytes(data)
+    with gzip.open(str(tmp_path / "z.fa.gz"), "wb") as f:
+        f.write(data)
+    a, b = kmers.count_all(str(tmp_path / "p.fa"), 5, 9), kmers.count_all(str(tmp_path / "z.fa.gz"), 5, 9)
+    assert np.array_equal(a.block, b.block) and (a.n_bases, a.n_records) == (b.n_bases, b.n_records)
+    (tmp_path / "bad.fa").write_bytes(b"not fasta\n>x\nACGT\n")
+    with pytest.raises(_lib.SwgaError, match="not a FASTA image"):
+        kmers.count_all(str(tmp_path / "bad.fa"), 5, 9)
+    (tmp_path / "q.fq").write_bytes(b"@r1\nACGT\n+\nIIII\n")
+    with pytest.raises(_lib.SwgaError, match="FASTQ"):
+        kmers.count_all(str(tmp_path / "q.fq"), 5, 9)
+    (tmp_path / "empty.fa").write_bytes(b"")
+    e = kmers.count_all(str(tmp_path / "empty.fa"), 5, 9)
+    assert e.n_bases == 0 and not e.block.any()
