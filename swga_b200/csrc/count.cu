@@ -175,25 +175,33 @@ __global__ void __launch_bounds__(256)
 k_fold_tiled(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int k)
 {
     __shared__ uint32_t t1[64][65], t2[64][65];
+    __shared__ uint8_t rc3[64];                                // reverse complement of a 3-digit code
     const int md = k - 6, sh = 2 * (k - 3);
     const uint32_t M = blockIdx.x, rM = md ? rc_code(M, md) : 0u;
     if (M > rM) return;                                        // handled by the block of rc(M)
     const bool self = M == rM;
-    for (uint32_t i = threadIdx.x; i < 4096; i += 256) {
-        const uint32_t A = i >> 6, B = i & 63;
-        t1[A][B] = fwd[((uint64_t)A << sh) | (M << 6) | B];
-        if (!self) t2[A][B] = fwd[((uint64_t)A << sh) | (rM << 6) | B];
+    if (threadIdx.x < 64) rc3[threadIdx.x] = (uint8_t)rc_code(threadIdx.x, 3);
+    const uint32_t B = threadIdx.x & 63, A0 = threadIdx.x >> 6;   // this thread: column B, rows A0, A0 + 4, ...
+    const uint32_t *src1 = fwd + ((M << 6) | B), *src2 = fwd + ((rM << 6) | B);
+#pragma unroll 4
+    for (uint32_t A = A0; A < 64; A += 4) {
+        t1[A][B] = src1[(uint64_t)A << sh];
+        if (!self) t2[A][B] = src2[(uint64_t)A << sh];
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 4096; i += 256) {
-        const uint32_t A = i >> 6, B = i & 63, rA = rc_code(A, 3), rB = rc_code(B, 3);
+    const uint32_t rB = rc3[B];
+    const uint32_t x1 = (M << 6) | B, x2 = (rM << 6) | B;      // codes without their A digits
+    const uint32_t r1 = (rB << sh) | (rM << 6), r2 = (rB << sh) | (M << 6);   // partners without their last 3 digits
+#pragma unroll 4
+    for (uint32_t A = A0; A < 64; A += 4) {
+        const uint32_t rA = rc3[A];
         {
-            const uint32_t x = (A << sh) | (M << 6) | B, r = (rB << sh) | (rM << 6) | rA;
+            const uint32_t x = (A << sh) | x1, r = r1 | rA;
             const uint32_t v = t1[A][B], pv = self ? t1[rB][rA] : t2[rB][rA];
             canon[x] = x < r ? v + pv : (x == r ? v : 0u);
         }
         if (!self) {
-            const uint32_t x = (A << sh) | (rM << 6) | B, r = (rB << sh) | (M << 6) | rA;
+            const uint32_t x = (A << sh) | x2, r = r2 | rA;
             const uint32_t v = t2[A][B], pv = t1[rB][rA];
             canon[x] = x < r ? v + pv : (x == r ? v : 0u);
         }
