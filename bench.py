@@ -299,8 +299,8 @@ def run_b200_arm(args):
             if ev is not None:
                 ev[1].record()
             # accumulate = k_bucket_hist (sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count
-            # when the partitioned path applies (>= 2^22 starts, kmax 11 or 12), else the single k_count
-            acc = 5 if (self.n_starts >= (1 << 22) and 8 <= 2 * KMAX - 14 <= 10) else 1
+            # when the partitioned path applies (>= 14 Mi starts, kmax 11 or 12), else the single k_count
+            acc = 5 if (self.n_starts >= (14 << 20) and 8 <= 2 * KMAX - 14 <= 10) else 1
             # + k_marginalize per level + k_fold (k < 10) + k_fold_tiled per k >= 10
             self.launches = k + acc + (KMAX - KMIN) + (1 if KMIN < 10 else 0) + max(0, KMAX - max(KMIN, 10) + 1)
 

@@ -273,6 +273,8 @@ k_bench_atom_shared(uint32_t mask, uint64_t ops_per_thread, uint32_t *__restrict
     if (threadIdx.x == 0) atomicAdd(sink, sh[0]);
 }
 
+#define PT_AUTO_MIN_STARTS (14ull << 20)                    // auto mode: partitioned path from here on
+
 int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n_starts,
                                       int kmin, int kmax, uint32_t *d_tables, cudaStream_t stream, int *done);
 
@@ -351,10 +353,11 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     if (n_starts == 0) return SWGA_OK;
     cudaStream_t st = as_stream(stream);
     const TableOffs offs = swga_make_offs(kmin, kmax);
-    // Partitioned shared-memory path when the shape allows it (count_part.cu), else direct L2 reds.
+    // Partitioned shared-memory path when the shape allows it (count_part.cu) and the input is large enough to
+    // pay for its five launches (measured crossover with the direct kernel: 13 M starts), else direct L2 reds.
     // (Running the two concurrently on split ranges was measured in round 1 and does not overlap: both
     // are limited by the per-SM LSU issue path -- profiles/r01_summary.md.)
-    if (ctx->count_impl != 1) {
+    if (ctx->count_impl == 2 || (ctx->count_impl == 0 && n_starts >= PT_AUTO_MIN_STARTS)) {
         int done = 0;
         TRY(swga_count_accumulate_partitioned(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, st, &done));
         if (done) return SWGA_OK;

@@ -29,6 +29,8 @@ def main():
     seq[cut - 5:cut + 9] = ord("N")
     seq[1_000_000:1_000_700] = ord("A")
     rs = np.array([0, 31, 2_000_000, cut + 3, 7_000_001, n], dtype=np.uint64)
+    from swga_b200 import _lib
+    _lib.check(_lib.load().swga_ctx_set_count_impl(_lib.context(dev).h, 2))      # 4.7 Mbp shards: force the partitioned kernel
     for mode_b in (False, True):
         sh = dist.shard_genome(seq, rs, rank, world, kmax=12)
         d = torch.from_numpy(np.ascontiguousarray(sh.seq)).cuda()
@@ -39,6 +41,7 @@ def main():
         if rank == 0:
             want = O.count_dense_allk(seq, rs, 5, 12, mode_b=int(mode_b))
             assert np.array_equal(canon.cpu().numpy().view(np.uint32), want), mode_b
+    _lib.check(_lib.load().swga_ctx_set_count_impl(_lib.context(dev).h, 0))
     # ---- scoring: every rank scores its contiguous share of the sets; together they equal the unsharded result ----
     g = fasta.Genome(seq[:3_000_000].copy(), np.array([0, 1_200_000, 3_000_000], dtype=np.uint64), ["a", "b"])
     gi = locate.GenomeIndex(g)
