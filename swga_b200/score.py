@@ -252,11 +252,20 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
         if return_device:
             return ScoreResult(n_sites=o_n, fg_max_dist=o_max, fg_dist_mean=o_mean, fg_dist_std=o_std,
                                fg_dist_gini=o_gini, score=o_score, status=o_status)
-        status = o_status.cpu().numpy()
+        outs = (o_n, o_max, o_mean, o_std, o_gini, o_score, o_status)
+        if S <= (1 << 17):
+            # block-sized calls (the find_sets loop): results come back through pinned host tensors (torch caches
+            # pinned blocks, so no allocation after the first calls), seven copies in flight and ONE synchronisation;
+            # the arrays returned are views of those tensors
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True) for t in outs]
+            torch.cuda.current_stream().synchronize()
+        else:
+            host = [t.cpu() for t in outs]                    # one-shot bulk call: pinning 41 B/set would cost more than it saves
+        h_n, h_max, h_mean, h_std, h_gini, h_score, status = (t.numpy() for t in host)
         res = ScoreResult(
-            n_sites=o_n.cpu().numpy().view(np.uint32), fg_max_dist=o_max.cpu().numpy().view(np.uint32).astype(np.int64),
-            fg_dist_mean=o_mean.cpu().numpy(), fg_dist_std=o_std.cpu().numpy(), fg_dist_gini=o_gini.cpu().numpy(),
-            score=o_score.cpu().numpy(), passed=(status & 1).astype(bool), status=status)
+            n_sites=h_n.view(np.uint32), fg_max_dist=h_max.view(np.uint32).astype(np.int64),
+            fg_dist_mean=h_mean, fg_dist_std=h_std, fg_dist_gini=h_gini,
+            score=h_score, passed=(status & 1).astype(bool), status=status)
         # sets whose largest gap exceeds the in-kernel histogram: exact Gini through the sort path
         todo = np.nonzero(((status & 2) != 0) & ((status & 1) != 0))[0]
         bg = d_bg.cpu().numpy() if len(todo) else None
