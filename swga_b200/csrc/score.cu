@@ -361,12 +361,21 @@ struct GapAcc {
     uint32_t cnt, maxgap;
     unsigned long long sumsq;
 };
-__device__ __forceinline__ void add_gap(GapAcc &g, uint32_t gap, uint32_t *hist, uint32_t hist_bins)
+// `hist_s` is the 32-bit shared-memory address of the gap histogram: the predicated red keeps the loop bodies free
+// of a branch and of the generic-to-shared address arithmetic the compiler otherwise repeats per iteration.
+__device__ __forceinline__ void add_gap(GapAcc &g, uint32_t gap, uint32_t hist_s, uint32_t hist_bins)
 {
     ++g.cnt;
     g.sumsq += (unsigned long long)gap * gap;
     g.maxgap = max(g.maxgap, gap);
-    if (gap < hist_bins) atomicAdd(&hist[gap], 1u);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], 1;\n\t}"
+                 ::"r"(gap), "r"(hist_bins), "r"(hist_s + 4u * gap) : "memory");
+}
+// one bit of a shared-memory bitmap, when idx < len
+__device__ __forceinline__ void set_bit_if(uint32_t idx, uint32_t len, uint32_t bm_s, uint32_t p)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, %1;\n\t@p red.shared.or.b32 [%2], %3;\n\t}"
+                 ::"r"(idx), "r"(len), "r"(bm_s + 4u * (p >> 5)), "r"(1u << (p & 31)) : "memory");
 }
 
 __global__ void __launch_bounds__(DT_THREADS, 1)
@@ -386,6 +395,7 @@ k_score_dense(ScoreArgs a)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *bm = bm_all + warp * DT_WORDS;
     const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + warp * DT_LIST_CAP);
+    const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
     for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
@@ -457,12 +467,8 @@ k_score_dense(ScoreArgs a)
                 const uint32_t v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
                 const uint32_t first_idx = 8u * half - (lo & 3u);          // index in the segment of v[0] (may wrap below 0)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (first_idx + q < len) {                             // unsigned: also false before the segment
-                        const uint32_t p = v[q] - tile_base;
-                        atomicOr(&bm[p >> 5], 1u << (p & 31));
-                    }
-                }
+                for (int q = 0; q < 8; ++q)                                // unsigned compare: also false before the segment
+                    set_bit_if(first_idx + q, len, bm_s, (v[q] - tile_base) & ((1u << DT_SHIFT) - 1u));
             }
             while (need) {                                                 // what the chunks do not cover
                 const int l = __ffs(need) - 1;
@@ -520,7 +526,7 @@ k_score_dense(ScoreArgs a)
                     const uint32_t prev1 = j ? tile_base + lds_u16(cl_s + 2u * j - 2u) + 1 : carry;
                     if (prev1) {
                         const uint32_t gap = cur - (prev1 - 1);
-                        add_gap(acc, gap, hist, a.hist_bins);
+                        add_gap(acc, gap, hist_s, a.hist_bins);
                     } else {
                         first = cur + 1;
                     }
@@ -549,7 +555,7 @@ k_score_dense(ScoreArgs a)
                         v &= v - 1;
                         if (pred) {
                             const uint32_t gap = cur - (pred - 1);
-                            add_gap(acc, gap, hist, a.hist_bins);
+                            add_gap(acc, gap, hist_s, a.hist_bins);
                             } else {
                             first = cur + 1;
                         }
@@ -574,7 +580,7 @@ k_score_dense(ScoreArgs a)
                 if (!s_last[wv]) continue;
                 if (prev) {
                     const uint32_t gap = s_first[wv] - prev;              // both carry the + 1
-                    add_gap(x, gap, hist, a.hist_bins);
+                    add_gap(x, gap, hist_s, a.hist_bins);
                 }
                 prev = s_last[wv];
             }
