@@ -323,3 +323,26 @@ def test_file_image_gzip_and_errors(oracle, torch_cuda, tmp_path):
     (tmp_path / "empty.fa").write_bytes(b"")
     e = kmers.count_all(str(tmp_path / "empty.fa"), 5, 9)
     assert e.n_bases == 0 and not e.block.any()
+
+
+@pytest.mark.parametrize("n_small,big_len,want_b", [(10000, 1_000_001, True), (10001, 1_000_001, False),
+                                                    (0, 1_000_001, True), (0, 1_000_000, False)])
+def test_file_image_mode_choice_at_the_10001_record_limit(n_small, big_len, want_b, torch_cuda, tmp_path, monkeypatch):
+    """DSK looks at the first 10,001 records only (Bank.cpp:470-494): a record longer than 1 Mbp makes mode B when
+    it is among them and is not seen otherwise.  The file-image call decides from the head of the file, range batch
+    by range batch; the answer and the tables must equal the read-then-count path's."""
+    from swga_b200 import fasta, kmers, synth
+    monkeypatch.setenv("SWGA_FASTA_CHUNK", "65536")
+    big = synth.bases(31, 0, big_len, 0.5)
+    big[500:520] = ord("N")
+    with open(str(tmp_path / "m.fa"), "wb") as f:
+        for i in range(n_small):
+            f.write(b">s%d\nACGTTGCA\n" % i)
+        f.write(b">big\n")
+        body = big[:1_000_000].reshape(-1, 100)                      # 100-column lines (+ a last line of one base)
+        f.write(b"\n".join(bytes(r) for r in body) + b"\n" + bytes(big[1_000_000:]) + b"\n")
+    g = fasta.read_fasta(str(tmp_path / "m.fa"))
+    assert g.n_records == n_small + 1 and g.dsk_mode_b == want_b
+    a = kmers.count_all(str(tmp_path / "m.fa"), 5, 8)
+    assert a.mode_b == want_b and (a.n_bases, a.n_records) == (g.n_bases, g.n_records)
+    assert np.array_equal(a.block, kmers.count_all(g, 5, 8).block)
