@@ -99,3 +99,42 @@ def test_table_export_and_bed_files(tmp_path, oracle):
     curve = oracle.lorenz(oracle.seq_diff(oracle.linearize_binding_sites([{"a": [1, 30], "b": [5]}, {"a": [2, 30], "b": [5]}], ends)))
     assert out.getvalue() == "SetID\tCDF\n1\t" + ",".join(oracle.py2_float_str(v) for v in curve) + "\n"
     ws.close()
+
+
+def test_export_and_summary_commands_through_the_cli(tmp_path, capsys):
+    """`python -m swga_b200.commands --db X export ... | summary`: option wiring of the argparse front end on a
+    workspace filled through the workspace API (neither command touches the GPU)."""
+    from swga_b200 import commands, workspace
+    fg = tmp_path / "fg.fa"
+    fg.write_bytes(b">a\n" + b"ACGTTGCA" * 20 + b"\n>b\n" + b"GGATCCTA" * 10 + b"\n")
+    db = str(tmp_path / "p.db")
+    ws = workspace.Workspace(db)
+    ws.create_tables()
+    ws.metadata = dict(version=workspace.VERSION, fg_file=str(fg), bg_file="bg.fa", ex_file=None, fg_length=240, bg_length=5000)
+    ws.add_primers([dict(seq="ACGTT", fg_freq=20, bg_freq=3, ratio=20 / 3.0), dict(seq="GGATC", fg_freq=10, bg_freq=0, ratio=float("inf"))],
+                   add_revcomp=False)
+    ps = ws.primers()
+    ps[0].locations, ps[1].locations = {"a": [0, 8, 16], "b": []}, {"a": [], "b": [0, 8]}
+    for i, p in enumerate(ps):
+        p._id, p.active, p.tm = i + 1, True, 30.0 + i
+    ws.update_primers(ps)
+    ws.add_set(1, ["ACGTT", "GGATC"], 0.5, "f", set_size=2, bg_dist_mean=10.0, fg_dist_std=1.5, fg_dist_gini=0.1, fg_max_dist=40,
+               fg_dist_mean=12.5)
+    ws.close()
+    out = tmp_path / "primers.tsv"
+    assert commands.main(["--db", db, "export", "primers", "--output", str(out), "--order_by", "fg_freq", "--descending",
+                          "--limit", "1", "--unknown_option", "7"]) == 0
+    assert out.read_text() == "seq\tfg_freq\tbg_freq\tratio\tgini\ttm\nACGTT\t20\t3\t%r\t\t30.0\n" % (20 / 3.0)
+    assert commands.main(["--db", db, "export", "sets", "--no_header"]) == 0
+    assert capsys.readouterr().out == "1\t0.5\t2\t10.0\t40\t12.5\t1.5\t0.1\tf\tACGTT,GGATC\n"
+    assert commands.main(["--db", db, "export", "lorenz", "--ids", "1"]) == 0
+    lines = capsys.readouterr().out.splitlines()
+    assert lines[0] == "SetID\tCDF" and lines[1].startswith("1\t") and lines[1].endswith(",1.0")
+    assert commands.main(["--db", db, "export", "bedgraph", "--ids", "1", "--output_folder", str(tmp_path / "x"),
+                          "--window_size", "50", "--step_size", "25"]) == 0
+    bg = (tmp_path / "x" / "fg_export" / "set_1" / "set_1.bedgraph").read_text().splitlines()
+    assert bg[0] == "track type=bedGraph None" and bg[1] == "a 25 25 3"
+    assert commands.main(["--db", db, "summary"]) == 0
+    text = capsys.readouterr().out
+    assert "There are 2 primers in the database." in text and "The best scoring set is #1, with 2 primers" in text
+    assert "ranges between 30.00C and 31.00C" in text
