@@ -563,7 +563,7 @@ def scoring_extra(dev):
     g = fasta.Genome(synth.bases(seed, 0, n, gc), synth.equal_records(n, n_rec), ["chr%d" % (i + 1) for i in range(n_rec)])
     tabs = kmers.count_all(g, 5, 12)
     gi = locate.GenomeIndex(g)
-    out = {"unit": "sets/s", "fg_bases": n, "timing": "CUDA events, best of 3, device-resident inputs"}
+    out = {"unit": "sets/s", "fg_bases": n, "timing": "CUDA events, best of 3, device-resident inputs; e2e = host API (numpy in, numpy out), wall clock, best of 3"}
     t12 = tabs.table(12)
     order = np.argsort(-t12.astype(np.int64), kind="stable")
     lo = int(np.searchsorted(-t12[order].astype(np.int64), -400))
@@ -593,16 +593,22 @@ def scoring_extra(dev):
             st = res.status.cpu().numpy()
             # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
             h_bg = np.full(S, 1000.0)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            score.score_sets(sl, sets_, h_bg, max_fg)
-            torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
+            e2e_s = None
+            for _ in range(3):                                   # best of 3, like the device timing above
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                score.score_sets(sl, sets_, h_bg, max_fg)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                e2e_s = dt if e2e_s is None else min(e2e_s, dt)
+            n_pass = int((st & 1).sum())
+            # score.score_sets: bulk calls copy back status + max_dist of every set and the rest for the passing ones
+            d2h = S * 5 + n_pass * 44 if (S > (1 << 17) and 2 * n_pass <= S) else S * 41
             row[label] = {"sets_per_s": S / best * 1e3, "ms": best, "mean_unique_sites_per_set": float(L.mean()),
                           "passed_frac": float((st & 1).mean()),
                           "merged_sites_per_s": float(sl.counts()[:-1].mean()) * 8 * S / best * 1e3,
                           "e2e_sets_per_s": S / e2e_s, "e2e_h2d_bytes": int(mapped_host.nbytes + h_bg.nbytes),
-                          "e2e_d2h_bytes": int(S * 41)}
+                          "e2e_d2h_bytes": int(d2h)}
         out[name] = row
     return out
 

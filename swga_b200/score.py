@@ -215,7 +215,8 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
     bg_dist_mean  float64 [S]
     Returns arrays: n_sites, fg_max_dist, fg_dist_mean, fg_dist_std, fg_dist_gini, score (default
     expression), passed (bool).  Sets that fail the max_dist filter (non-interactive) keep their
-    max_dist; their other variables are not meaningful, as in score.py:89-90.
+    max_dist; their other variables are not meaningful, as in score.py:89-90 (bulk calls do not even
+    copy them back: they read 0).
     """
     import torch
     sl = site_lists
@@ -259,9 +260,22 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
             # the arrays returned are views of those tensors
             host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True) for t in outs]
             torch.cuda.current_stream().synchronize()
+            h_n, h_max, h_mean, h_std, h_gini, h_score, status = (t.numpy() for t in host)
         else:
-            host = [t.cpu() for t in outs]                    # one-shot bulk call: pinning 41 B/set would cost more than it saves
-        h_n, h_max, h_mean, h_std, h_gini, h_score, status = (t.numpy() for t in host)
+            # bulk call: status and max_dist of every set; the other 36 bytes per set only for the sets that passed
+            # (with the default max_fg_bind_dist most candidate sets are rejected), scattered into zero-filled
+            # arrays whose untouched pages are never materialised
+            status, h_max = o_status.cpu().numpy(), o_max.cpu().numpy()
+            n_pass = int(np.count_nonzero(status & 1))
+            if 2 * n_pass > S:
+                h_n, h_mean, h_std, h_gini, h_score = (t.cpu().numpy() for t in (o_n, o_mean, o_std, o_gini, o_score))
+            else:
+                sel = torch.nonzero(o_status & 1).squeeze(1)
+                idx = sel.cpu().numpy()
+                h_n = np.zeros(S, dtype=np.int32)
+                h_mean, h_std, h_gini, h_score = (np.zeros(S, dtype=np.float64) for _ in range(4))
+                for dst, src in ((h_n, o_n), (h_mean, o_mean), (h_std, o_std), (h_gini, o_gini), (h_score, o_score)):
+                    dst[idx] = src[sel].cpu().numpy()
         res = ScoreResult(
             n_sites=h_n.view(np.uint32), fg_max_dist=h_max.view(np.uint32).astype(np.int64),
             fg_dist_mean=h_mean, fg_dist_std=h_std, fg_dist_gini=h_gini,
