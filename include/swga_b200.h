@@ -79,7 +79,8 @@ uint64_t swga_brk_words(uint64_t n_bases);                 /* uint32 words of th
 /* ---- host-side FASTA reader (native host code; no GPU) ---------------------------------------
  * Replaces DSK's Bank::get_next_seq_from_file (ext/dsk/minia/Bank.cpp:150-209): records start at a
  * '>' or '@' that begins a line, lines are joined, one trailing '\r' per line is dropped under
- * Bank.cpp:124-125's rule.  Pass 1 (h_seq == NULL) returns sizes; pass 2 fills the buffers (it reuses the
+ * Bank.cpp:124-125's rule.  FASTQ records ('+' at a line start, Bank.cpp:192-201) are read with the
+ * reference's byte-level rules by one thread (any image that begins with '@' or holds such a line).  Pass 1 (h_seq == NULL) returns sizes; pass 2 fills the buffers (it reuses the
  * line ranges pass 1 found when it follows it on the same thread with the same, unmodified image).  Both
  * passes scan the image with up to 16 host threads.
  *   h_seq        [*n_bases]   joined sequence bytes of all records, no separators

@@ -89,68 +89,84 @@ void orc_count_allk(const uint8_t *seq, const uint64_t *rec_starts, uint32_t n_r
 }
 
 /*
- * FASTA reader restating Bank::get_next_seq_from_file (ext/dsk/minia/Bank.cpp:150-209) with
- * buffered_gets (Bank.cpp:77-128) on an in-memory file image.  FASTQ ('+' separator) is not
- * restated: a '+' at line start returns -2.  Bytes >= 0x80 that read as (signed char)-1
- * (0xFF) end the file as in the reference (Bank.cpp:66-72).
+ * FASTA / FASTQ reader restating Bank::get_next_seq_from_file (ext/dsk/minia/Bank.cpp:150-209) with
+ * buffered_getc / buffered_gets (Bank.cpp:66-72,77-128) on an in-memory file image.  A '+' at a line
+ * start ends the sequence and switches to the FASTQ branch (Bank.cpp:192-201): the rest of the '+' line
+ * is skipped, then quality lines are read into `dummy` -- which still holds the remainder of the header
+ * line (Bank.cpp:167, append = true) -- until dummy is at least as long as the read; the next header is
+ * then searched byte by byte (last_char = 0).  Bytes that read as (signed char)-1 (0xFF) end the file or
+ * the record exactly as in the reference.
  *
  * Writes the joined sequence bytes to seq_out (capacity >= n) and record boundaries to
  * rec_starts (capacity max_rec+1).  Returns the number of records, or <0 on error.
  */
 typedef struct { const uint8_t *b; uint64_t n, pos; } rd_t;
+typedef struct { uint8_t *s; uint64_t len, max; } vs_t;     /* variable_string_t */
 static int rd_getc(rd_t *r) {
     if (r->pos >= r->n) return -1;
     int c = (signed char)r->b[r->pos++];
     return c;            /* may itself be -1 for byte 0xFF, exactly like buffered_getc */
 }
-/* buffered_gets(..., allow_spaces): append up to the delimiter into out; returns the
- * delimiter char in *dret (0 if EOF hit first); -1 if already at EOF before reading. */
-static int64_t rd_gets(rd_t *r, uint8_t *out, uint64_t *len, int allow_spaces, int *dret,
-                       int store)
+/* buffered_gets(bf, s, dret, append, allow_spaces): appends up to the delimiter ('\n', or any isspace()
+ * byte when !allow_spaces); *dret = the delimiter (0 if the end of the file came first); returns the
+ * length of s, or -1 when already at the end of the file.  `fixed`: s->s is the caller's large buffer. */
+static int64_t rd_gets(rd_t *r, vs_t *s, int *dret, int append, int allow_spaces, int fixed)
 {
     if (dret) *dret = 0;
+    if (!append) s->len = 0;
     if (r->pos >= r->n) return -1;
     uint64_t i = r->pos;
     if (allow_spaces) { while (i < r->n && r->b[i] != '\n') i++; }
     else              { while (i < r->n && !isspace(r->b[i])) i++; }
-    if (store) memcpy(out + *len, r->b + r->pos, i - r->pos);
-    *len += i - r->pos;
+    if (!fixed && s->max < s->len + (i - r->pos) + 1) {
+        s->max = 2 * (s->len + (i - r->pos) + 1);
+        s->s = (uint8_t *)realloc(s->s, s->max);
+    }
+    memcpy(s->s + s->len, r->b + r->pos, i - r->pos);
+    s->len += i - r->pos;
     r->pos = i;
     if (i < r->n) { if (dret) *dret = r->b[i]; r->pos = i + 1; }
-    if (store && allow_spaces && *len > 1 && out[*len - 1] == '\r') (*len)--;   /* Bank.cpp:124-125 */
-    return (int64_t)*len;
+    if (allow_spaces && s->len > 1 && s->s[s->len - 1] == '\r') s->len--;      /* Bank.cpp:124-125 */
+    return (int64_t)s->len;
 }
 
 int64_t orc_fasta_parse(const uint8_t *buf, uint64_t n, uint8_t *seq_out,
                         uint64_t *rec_starts, uint64_t max_rec)
 {
     rd_t r = {buf, n, 0};
+    vs_t header = {NULL, 0, 0}, dummy = {NULL, 0, 0};
     int last_char = 0, c;
     uint64_t total = 0, nrec = 0;
-    uint64_t hl;
+    int64_t ret = 0;
     for (;;) {
         if (last_char == 0) {                                       /* Bank.cpp:154-160 */
             while ((c = rd_getc(&r)) != -1 && c != '>' && c != '@') {}
             if (c == -1) break;
             last_char = c;
         }
-        hl = 0;
-        if (rd_gets(&r, NULL, &hl, 0, &c, 0) < 0) break;            /* header token */
-        if (c != '\n') { hl = 0; rd_gets(&r, NULL, &hl, 1, NULL, 0); }  /* rest of header */
-        if (nrec >= max_rec) return -3;
+        dummy.len = 0;                                              /* Bank.cpp:161 */
+        if (rd_gets(&r, &header, &c, 0, 0, 0) < 0) break;           /* header token */
+        if (c != '\n') rd_gets(&r, &dummy, NULL, 1, 1, 0);          /* rest of the header line, into dummy */
+        if (nrec >= max_rec) { ret = -3; break; }
         rec_starts[nrec] = total;
-        uint64_t len = 0;
-        uint8_t *read = seq_out + total;
+        vs_t read = {seq_out + total, 0, 0};
         while ((c = rd_getc(&r)) != -1 && c != '>' && c != '+' && c != '@') {
             if (c == '\n') continue;                                /* empty line */
-            read[len++] = (uint8_t)c;
-            rd_gets(&r, read, &len, 1, NULL, 1);
+            read.s[read.len++] = (uint8_t)c;
+            rd_gets(&r, &read, NULL, 1, 1, 1);
         }
-        if (c == '+') return -2;
         if (c == '>' || c == '@') last_char = c;
-        total += len;
+        if (c == '+') {                                             /* fastq, Bank.cpp:192-201 */
+            while ((c = rd_getc(&r)) != -1 && c != '\n') {}         /* rest of the quality comment */
+            while (rd_gets(&r, &dummy, NULL, 1, 1, 0) >= 0 && dummy.len < read.len) {}
+            last_char = 0;
+        }
+        total += read.len;
         nrec++;
     }
+    free(header.s);
+    free(dummy.s);
+    if (ret < 0) return ret;
     rec_starts[nrec] = total;
     return (int64_t)nrec;
 }

@@ -42,10 +42,12 @@ def build(force=False, verbose=False):
     return LIB
 
 
-def build_set_finder(ref="/root/reference"):
+def build_set_finder(ref=None):
     """Compile the reference's set_finder (cliquer + swga front end) UNCHANGED from its own sources,
-    where they lie, into swga_b200/bin/ -- the host remainder of the path.  Returns the path, or None
-    when neither a prebuilt binary nor the reference sources are available."""
+    where they lie, into swga_b200/bin/ -- the host remainder of the path.  `ref` (default: $SWGA_REFERENCE,
+    else /root/reference) is a checkout of eclarke/swga.  Returns the path, or None when neither a prebuilt
+    binary nor the reference sources are available (sets.set_finder() then says what to do)."""
+    ref = ref or os.environ.get("SWGA_REFERENCE") or "/root/reference"
     out = os.path.join(HERE, "bin", "set_finder")
     if os.access(out, os.X_OK):
         return out

@@ -14,9 +14,10 @@
 
 Option names and defaults are the reference's (`commands/specfiles/*.yaml`).  Prompts (`click.confirm`)
 become the `force` argument: without it a command that would delete rows raises instead of asking.
-Melting temperatures come from the third-party `melt` package in the reference (parity unpinned,
-SURVEY.md 8c): `filter` applies the Tm range only to primers whose `tm` column is already filled
-(e.g. by the reference) or when a `tm_fn` is supplied.
+Melting temperatures come from the third-party `melt` package in the reference (source not vendored: parity
+unpinned); `swga_b200/melting.py` restates the published nearest-neighbour method it documents and
+`filter` / `activate` fill in missing `tm` values with it (or with a caller's `tm_fn`) before the Tm range is
+applied, as Primers.filter_tm_range does (primers.py:151-165).
 
     python -m swga_b200.commands count --min_size 5 --max_size 12 ...      (inside a workspace directory)
 """
@@ -185,17 +186,20 @@ def filter(db_name=workspace.DEFAULT_DB_FNAME, max_primers=200, min_fg_bind=None
             n1 = len(ps)
             ps = [p for p in ps if p.bg_freq <= max_bg_bind]
             message("{}/{} primers bind the background genome <= {} times".format(len(ps), n1, max_bg_bind))
-            if tm_fn is not None:
-                for p in ps:
-                    if p.tm is None:
-                        p.tm = tm_fn(p.seq)
-                ws.update_primers(ps, fields=("tm",))
-            if tm_fn is not None or all(p.tm is not None for p in ps):
-                n2 = len(ps)
-                ps = [p for p in ps if min_tm <= p.tm <= max_tm]
-                message("{}/{} primers have a melting temp between {} and {} C".format(len(ps), n2, min_tm, max_tm))
-            else:
-                message("melting temperatures are not available (third-party `melt`): Tm range not applied")
+            # filter_tm_range (primers.py:151-165): missing melting temperatures are computed first
+            # (update_melt_temps, primers.py:241-253), then the range is ALWAYS applied
+            if tm_fn is None:
+                from . import melting
+                tm_fn = melting.temp
+            todo = [p for p in ps if p.tm is None]
+            if todo:
+                message("Finding melting temps for {} primers...".format(len(todo)))
+                for p in todo:
+                    p.tm = tm_fn(p.seq)
+                ws.update_primers(todo, fields=("tm",))
+            n2 = len(ps)
+            ps = [p for p in ps if min_tm <= p.tm <= max_tm]
+            message("{}/{} primers have a melting temp between {} and {} C".format(len(ps), n2, min_tm, max_tm))
             ps = pipeline.limit_to(ps, max_primers) if ps else []
             gindex = gindex or locate.genome_index(meta["fg_file"])
             pipeline.update_locations(ps, gindex)
@@ -205,12 +209,15 @@ def filter(db_name=workspace.DEFAULT_DB_FNAME, max_primers=200, min_fg_bind=None
             ps = [p for p in ps if p.gini <= max_gini]
             message("{}/{} primers have a Gini coefficient <= {}".format(len(ps), n3, max_gini))
             primers = ps
-        # Primers.activate(max_primers): mark, at most max_primers
-        primers = primers[:max_primers]
+        # Primers.activate(min_active=max_primers) (primers.py:275-290): EVERY primer left is marked; the argument
+        # is only the number below which the note is printed
         for p in primers:
             p.active = True
         ws.update_primers(primers, fields=("active",))
         message("Marked {} primers as active.".format(len(primers)))
+        if len(primers) < max_primers:
+            message("Note: Fewer than {} primers were selected ({} passed all the filters). You may want to try "
+                    "less restrictive filtering parameters.".format(max_primers, len(primers)))
         return [p.seq for p in primers]
 
 
@@ -316,9 +323,9 @@ def export(what="sets", db_name=workspace.DEFAULT_DB_FNAME, output=None, order_b
 
 
 def activate(input, db_name=workspace.DEFAULT_DB_FNAME, reset=False, tm_fn=None, gindex=None):
-    """Activate.run (commands/activate.py:6-18): fill in melting temperatures (when a `tm_fn` is supplied: the
-    reference's comes from the third-party `melt`) and binding locations of the listed primers, mark them active.
-    `reset` is accepted and, as in the reference, not used."""
+    """Activate.run (commands/activate.py:6-18): fill in melting temperatures (swga_b200.melting unless a `tm_fn`
+    is supplied) and binding locations of the listed primers, mark them active.  `reset` is accepted and, as in
+    the reference, not used."""
     ws, meta = _open(db_name)
     with ws:
         with open(input) as f:
@@ -328,11 +335,13 @@ def activate(input, db_name=workspace.DEFAULT_DB_FNAME, reset=False, tm_fn=None,
         for s_ in seqs:
             if s_ not in have:
                 message(s_ + " not in the database; skipping. Add it manually with `swga count --input <file>` ")
-        if tm_fn is not None:
-            todo = [p for p in ps if p.tm is None]
-            for p in todo:
-                p.tm = tm_fn(p.seq)
-            ws.update_primers(todo, fields=("tm",))
+        if tm_fn is None:
+            from . import melting
+            tm_fn = melting.temp
+        todo = [p for p in ps if p.tm is None]
+        for p in todo:
+            p.tm = tm_fn(p.seq)
+        ws.update_primers(todo, fields=("tm",))
         todo = [p for p in ps if p.locations is None]
         if todo:
             message("Finding binding locations for {} primers...".format(len(todo)))

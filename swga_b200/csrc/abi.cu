@@ -28,6 +28,19 @@ extern "C" const char *swga_last_error(void) { return g_err; }
 extern "C" int swga_abi_version(void) { return 1; }
 
 // ---- context --------------------------------------------------------------------------------
+static int ctx_init_streams(swga_ctx *c)
+{
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    return SWGA_OK;
+}
+
+extern "C" void swga_ctx_destroy(swga_ctx *c);
+
 extern "C" int swga_ctx_create(int device, swga_ctx **out)
 {
     ARG_CHECK(out);
@@ -39,21 +52,19 @@ extern "C" int swga_ctx_create(int device, swga_ctx **out)
         return SWGA_E_CUDA;
     }
     CUDA_TRY(cudaSetDevice(device));
-    swga_ctx *c = new swga_ctx();
-    c->device = device;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) {
         swga_set_error("device %d is sm_%d%d; libswga_b200 is built for sm_100a only", device, prop.major, prop.minor);
-        delete c;
         return SWGA_E_CUDA;
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    swga_ctx *c = new swga_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    const int rc = ctx_init_streams(c);
+    if (rc != SWGA_OK) {                                       // nothing half-built is handed out or leaked
+        swga_ctx_destroy(c);
+        return rc;
     }
     *out = c;
     return SWGA_OK;
@@ -181,7 +192,7 @@ extern "C" int swga_stream_sync(swga_ctx *ctx, void *stream)
 //     is a header line; every other non-empty line is sequence and is appended whole
 //   * after appending a line, one trailing '\r' is dropped if the record is then longer than one
 //     byte (Bank.cpp:124-125)
-//   * '+' at line start would switch the reference to FASTQ: rejected here
+//   * '+' at line start switches the reference to its FASTQ branch: such files go to scan_sequential below
 static inline bool is_rec_start(uint8_t c) { return c == '>' || c == '@' || c == 0xFF; }
 
 // One contiguous range of LINES of the image, [pos, end) with pos at a line start.  `rec_len` enters as the
@@ -273,6 +284,101 @@ static void cut_ranges(const uint8_t *f, uint64_t n, unsigned n_rg, std::vector<
     }
 }
 
+// ---- sequential reader: FASTQ and mixed files ---------------------------------------------------
+// The line-parallel scanner above covers FASTA.  A '+' at a line start switches the reference to its FASTQ branch
+// (Bank.cpp:192-201), whose quality lines may begin with '>' or '@' and whose end depends on the length of the
+// read AND of the rest of the header line (the reference reads both into the same string): that cannot be cut
+// into independent ranges, so such files -- and every file that begins with '@' -- are read by one thread with the
+// reference's own byte-level rules.  Outputs may be NULL (sizes only).
+namespace {
+struct ByteCursor {
+    const uint8_t *b;
+    uint64_t n, pos;
+    int getc() { return pos < n ? (int)(signed char)b[pos++] : -1; }     // 0xFF reads as -1, like buffered_getc
+    bool at_end() const { return pos >= n; }
+    // buffered_gets(.., allow_spaces = true): the bytes up to the next '\n' (consumed) or the end of the file
+    uint64_t line(const uint8_t **start)
+    {
+        const uint8_t *p = b + pos;
+        const uint8_t *nl = static_cast<const uint8_t *>(memchr(p, '\n', n - pos));
+        const uint64_t len = nl ? (uint64_t)(nl - p) : n - pos;
+        *start = p;
+        pos += len + (nl ? 1 : 0);
+        return len;
+    }
+};
+// the '\r' rule of buffered_gets on a string that grows by appending (Bank.cpp:124-125)
+inline void drop_cr(std::vector<uint8_t> &s)
+{
+    if (s.size() > 1 && s.back() == '\r') s.pop_back();
+}
+}   // namespace
+
+static void scan_sequential(const uint8_t *f, uint64_t n, uint8_t *h_seq, uint64_t *h_rec_starts, uint64_t *h_hdr,
+                            uint64_t *n_bases, uint64_t *n_rec)
+{
+    ByteCursor cur{f, n, 0};
+    std::vector<uint8_t> dummy;                                // rest of the header line, then the quality lines
+    uint64_t total = 0, rec = 0;
+    int last_char = 0, c;
+    for (;;) {
+        if (last_char == 0) {                                  // Bank.cpp:154-160: next header, byte by byte
+            while ((c = cur.getc()) != -1 && c != '>' && c != '@') {}
+            if (c == -1) break;
+            last_char = c;
+        }
+        if (cur.at_end()) break;                               // nothing after the header mark: no record
+        const uint64_t hdr_pos = cur.pos;
+        uint64_t q = cur.pos;                                  // header token: up to the first isspace() byte
+        while (q < n && !isspace(f[q])) ++q;
+        dummy.clear();
+        cur.pos = q < n ? q + 1 : n;
+        if (q < n && f[q] != '\n' && !cur.at_end()) {
+            const uint8_t *st;
+            const uint64_t l = cur.line(&st);
+            dummy.assign(st, st + l);
+            drop_cr(dummy);
+        }
+        if (h_rec_starts) h_rec_starts[rec] = total;
+        if (h_hdr) {
+            const uint8_t *nl = static_cast<const uint8_t *>(memchr(f + hdr_pos, '\n', n - hdr_pos));
+            h_hdr[2 * rec] = hdr_pos;
+            h_hdr[2 * rec + 1] = (nl ? (uint64_t)(nl - f) : n) - hdr_pos;
+        }
+        uint64_t len = 0;                                      // this record's bases so far
+        while ((c = cur.getc()) != -1 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n') continue;                           // empty line
+            const bool alone_at_eof = cur.at_end();            // gets() finds the end of the file: no '\r' rule
+            --cur.pos;                                         // the byte just taken is the first of its line
+            const uint8_t *st;
+            const uint64_t l = cur.line(&st);
+            // the dropped '\r' is never written: the byte after this record's share of h_seq is not ours
+            const uint64_t drop = (!alone_at_eof && len + l > 1 && st[l - 1] == '\r') ? 1 : 0;
+            if (h_seq) memcpy(h_seq + total + len, st, l - drop);
+            len += l - drop;
+        }
+        if (c == '>' || c == '@') last_char = c;
+        if (c == '+') {                                        // Bank.cpp:192-201
+            while ((c = cur.getc()) != -1 && c != '\n') {}     // rest of the quality comment
+            while (!cur.at_end()) {                            // quality, appended to the rest of the header line
+                const uint8_t *st;
+                const uint64_t l = cur.line(&st);
+                dummy.insert(dummy.end(), st, st + l);
+                drop_cr(dummy);
+                if (dummy.size() >= len) break;
+            }
+            last_char = 0;
+        }
+        total += len;
+        ++rec;
+    }
+    if (h_rec_starts) h_rec_starts[rec] = total;
+    *n_bases = total;
+    *n_rec = rec;
+}
+
+static bool needs_sequential(const uint8_t *f, uint64_t n) { return n > 0 && f[0] == '@'; }
+
 // Both passes (sizes, then fill) run on up to 16 host threads: the image is cut at line starts into ranges that
 // are scanned independently (a line never depends on another one except through "is the record still empty",
 // which a range recovers by looking at the lines before its start), then prefix sums place every range.
@@ -284,6 +390,10 @@ extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uin
         swga_set_error("not a FASTA image: first byte is 0x%02x, expected '>' (DSK would read it as a list of file names)",
                        f[0]);
         return SWGA_E_FORMAT;
+    }
+    if (needs_sequential(f, n)) {                                // FASTQ (or '@' headers): the byte-level reader
+        scan_sequential(f, n, h_seq, h_rec_starts, h_hdr, n_bases, n_rec);
+        return SWGA_OK;
     }
     unsigned hw = std::thread::hardware_concurrency();
     const char *env_chunk = getenv("SWGA_FASTA_CHUNK");          // bytes per range at least (tests force small ranges)
@@ -315,10 +425,10 @@ extern "C" int swga_fasta_scan(const uint8_t *f, uint64_t n, uint8_t *h_seq, uin
     if (!filling) last_rg = rg;
     uint64_t total = 0, rec = 0;
     for (unsigned t = 0; t < n_thr; ++t) {
-        if (rg[t].status != SWGA_OK) {
-            swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
-                           (unsigned long long)rg[t].bad_pos);
-            return SWGA_E_FORMAT;
+        if (rg[t].status != SWGA_OK) {                           // a FASTQ record inside a '>' file
+            last_f = nullptr;
+            scan_sequential(f, n, h_seq, h_rec_starts, h_hdr, n_bases, n_rec);
+            return SWGA_OK;
         }
         rg[t].base0 = total;
         rg[t].rec0 = rec;
@@ -589,10 +699,9 @@ static int decide_mode(const uint8_t *f, std::vector<ScanRange> &rg, unsigned n_
         std::vector<std::vector<uint64_t>> loc(r1 - r0);
         parallel_for(r1 - r0, n_thr, [&](unsigned j) { scan_range(f, rg[r0 + j], nullptr, nullptr, nullptr, &loc[j]); });
         for (unsigned j = 0; j < r1 - r0; ++j) {
-            if (rg[r0 + j].status != SWGA_OK) {
-                swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
-                               (unsigned long long)rg[r0 + j].bad_pos);
-                return SWGA_E_FORMAT;
+            if (rg[r0 + j].status != SWGA_OK) {                // a FASTQ record: the caller takes the byte-level reader
+                *mode = -2;
+                return SWGA_OK;
             }
             for (uint64_t l : loc[j]) {
                 const uint64_t s = total + l;
@@ -624,8 +733,36 @@ static int ensure_recs(swga_ctx *ctx, size_t want)
     return SWGA_OK;
 }
 
+// FASTQ and mixed files (scan_sequential): read by one host thread into a host buffer, then the host-buffer pipeline.
+static int count_fasta_sequential(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
+                                  uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used)
+{
+    uint64_t nb = 0, nr = 0;
+    scan_sequential(f, n_file, nullptr, nullptr, nullptr, &nb, &nr);
+    std::vector<uint8_t> seq(nb + 64);
+    std::vector<uint64_t> rs(nr + 1);
+    scan_sequential(f, n_file, seq.data(), rs.data(), nullptr, &nb, &nr);
+    if (mode < 0) mode = swga_dsk_mode(rs.data(), nr);
+    if (mode_used) *mode_used = mode;
+    if (n_bases) *n_bases = nb;
+    if (n_rec) *n_rec = nr;
+    TRY(swga_count_stream_host(ctx, seq.data(), nb, rs.data(), nr, mode, kmin, kmax, nb, d_fwd));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));              // `seq` and `rs` go out of scope
+    return SWGA_OK;
+}
+
+static int count_fasta_stream_impl(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
+                                   uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used, bool *fastq_midway);
+
 extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
                                        uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used)
+{
+    bool midway = false;
+    return count_fasta_stream_impl(ctx, f, n_file, mode, kmin, kmax, d_fwd, n_bases, n_rec, mode_used, &midway);
+}
+
+static int count_fasta_stream_impl(swga_ctx *ctx, const uint8_t *f, uint64_t n_file, int mode, int kmin, int kmax,
+                                   uint32_t *d_fwd, uint64_t *n_bases, uint64_t *n_rec, int *mode_used, bool *fastq_midway)
 {
     ARG_CHECK(ctx && (f || n_file == 0) && d_fwd && mode >= -1 && mode <= 1);
     if (kmin < 2 || kmax < kmin || kmax > SWGA_KMAX_LIMIT) {
@@ -648,8 +785,14 @@ extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t
     double t_fill = 0, t_wait = 0, t_enq = 0;
     const double t0 = now();
     std::vector<ScanRange> rg;
+    if (needs_sequential(f, n_file))
+        return count_fasta_sequential(ctx, f, n_file, mode, kmin, kmax, d_fwd, n_bases, n_rec, mode_used);
     cut_ranges(f, n_file, n_rg, rg);
-    if (mode < 0) TRY(decide_mode(f, rg, n_thr, &mode));
+    if (mode < 0) {
+        TRY(decide_mode(f, rg, n_thr, &mode));
+        if (mode == -2)                                        // a FASTQ record near the head of a '>' file
+            return count_fasta_sequential(ctx, f, n_file, -1, kmin, kmax, d_fwd, n_bases, n_rec, mode_used);
+    }
     const double t1 = now();
     if (mode_used) *mode_used = mode;
     const int mask_mode = mode ? SWGA_MASK_NONE : SWGA_MASK_N;
@@ -709,7 +852,12 @@ extern "C" int swga_count_fasta_stream(swga_ctx *ctx, const uint8_t *f, uint64_t
         for (unsigned j = 0; j < cnt; ++j) {
             const ScanRange &x = rg[r + j];
             if (x.status != SWGA_OK) {
-                swga_set_error("FASTQ input ('+' at the start of a line, byte %llu) is not supported",
+                // a FASTQ record ('+' at a line start) deep inside a '>' file: chunks before it are already being
+                // accumulated into d_fwd.  swga_count_fasta_host starts over with the byte-level reader; a caller
+                // of the accumulating call has to do the same on a fresh block.
+                *fastq_midway = true;
+                swga_set_error("FASTQ record ('+' at the start of a line, byte %llu) inside a FASTA image: d_fwd is partial; "
+                               "zero it and use swga_fasta_scan + swga_count_stream_host, or swga_count_fasta_host",
                                (unsigned long long)x.bad_pos);
                 return SWGA_E_FORMAT;
             }
@@ -778,7 +926,14 @@ extern "C" int swga_count_fasta_host(swga_ctx *ctx, const uint8_t *f, uint64_t n
     const bool trace = getenv("SWGA_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    TRY(swga_count_fasta_stream(ctx, f, n_file, mode, kmin, kmax, fwd, n_bases, n_rec, mode_used));
+    bool midway = false;
+    int rc = count_fasta_stream_impl(ctx, f, n_file, mode, kmin, kmax, fwd, n_bases, n_rec, mode_used, &midway);
+    if (rc == SWGA_E_FORMAT && midway) {                       // mixed FASTA / FASTQ image: start over, byte-level reader
+        CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+        CUDA_TRY(cudaMemsetAsync(fwd, 0, words * 4, ctx->s_comp));
+        rc = count_fasta_sequential(ctx, f, n_file, mode, kmin, kmax, fwd, n_bases, n_rec, mode_used);
+    }
+    TRY(rc);
     TRY(swga_count_finalize(ctx, kmin, kmax, fwd, ctx->s_comp));
     TRY(swga_fold_canonical(ctx, kmin, kmax, fwd, canon, ctx->s_comp));
     const double t1 = now();

@@ -204,6 +204,9 @@ def shard_sets(n_sets, rank, world):
     return lo, min(n_sets, lo + per)
 
 
+MAX_SET_SIZE = 31
+
+
 class ScoreResult(dict):
     __getattr__ = dict.__getitem__
 
@@ -229,6 +232,10 @@ def score_sets(site_lists, sets, bg_dist_mean, max_fg_bind_dist, interactive=Fal
         S, max_m = sets.shape
     else:
         S, max_m = d_sets.shape
+    if max_m > MAX_SET_SIZE:
+        # kernel (d) merges at most 32 lists per set: 31 primers + the record bounds (csrc/score.cu SC_MAX_LISTS);
+        # the reference has no limit, its default --max_size is 7 (find_sets.yaml:10-13)
+        raise ValueError("a primer set may hold at most %d primers on the device path, got %d" % (MAX_SET_SIZE, max_m))
     mfd = max_fg_bind_dist
     mfd = 0xFFFFFFFF if (mfd == float("inf") or mfd > 0xFFFFFFFF) else max(0, int(mfd))
     with torch.cuda.device(dev):
@@ -311,8 +318,11 @@ def default_score_set(expression, primer_set, primer_locs, max_dist, bg_dist_mea
     Returns (score, namespace).  The gap statistics come from the device kernel."""
     locs = np.asarray(list(primer_locs), dtype=np.int64)
     if len(np.unique(locs)) != len(locs):
-        raise NotImplementedError("default_score_set expects de-duplicated locations "
-                                  "(as linearize_binding_sites returns them)")
+        # Not what linearize_binding_sites hands over (it de-duplicates, locate.py:33), but the reference takes any
+        # list: stats.seq_diff keeps the zero gaps of repeated locations (stats.py:22-33).  The device kernel
+        # merges sorted-unique site lists, so this rare, tiny case is evaluated on the host with the same exact
+        # integer forms as the kernel (DESIGN.md 3d): mean = H/n, gini = (2F - (2P - H)) / 2F with F = floor(Hn/2).
+        return _score_duplicated_locations(expression, primer_set, locs, max_dist, bg_dist_mean)
     if len(locs) < 2:
         # the reference divides by zero in stats.mean/stdev here
         raise ZeroDivisionError("float division by zero")
@@ -326,6 +336,30 @@ def default_score_set(expression, primer_set, primer_locs, max_dist, bg_dist_mea
         raise ZeroDivisionError("float division by zero")        # stats.gini: fair_area == 0
     score = evaluate_expression(expression, namespace)
     return score, namespace
+
+
+def _score_duplicated_locations(expression, primer_set, locs, max_dist, bg_dist_mean):
+    gaps = np.diff(np.sort(locs)).astype(object)              # Python ints: no overflow, exact sums
+    n = len(gaps)
+    if n < 2:
+        raise ZeroDivisionError("float division by zero")
+    H = int(sum(gaps))
+    mean = float(H) / n                                        # stats.py:10-12
+    mu = H / float(n)
+    std = math.sqrt(sum((float(x) - mu) ** 2 for x in gaps) / (float(n) - 1.0))      # stats.py:15-19, in gap order
+    asc = sorted(gaps)
+    prefix = 0
+    two_area = 0
+    for v in asc:                                              # stats.py:46-52: area += height - v / 2.
+        prefix += v
+        two_area += 2 * prefix - v
+    fair = (H * n) // 2                                        # Python-2 floor division, stats.py:53
+    if fair == 0:
+        raise ZeroDivisionError("float division by zero")
+    gini = (fair - two_area / 2.0) / fair
+    namespace = {"set_size": len(primer_set), "fg_dist_mean": mean, "fg_dist_std": std, "fg_dist_gini": gini,
+                 "bg_dist_mean": bg_dist_mean, "fg_max_dist": max_dist}
+    return evaluate_expression(expression, namespace), namespace
 
 
 def score_set(primers, max_fg_bind_dist, bg_dist_mean, chr_ends, score_fun, interactive=False):

@@ -196,6 +196,10 @@ class Workspace(object):
         primer_seqs = list(primer_seqs)
         if not primer_seqs:
             raise ValueError("Cannot add an empty set.")
+        if isinstance(score, float) and score != score:
+            # `score REAL NOT NULL` (workspace.py:171): a NaN can only come from 0/0 in the statistics, where the
+            # reference has already raised (stats.py:53-54 gini with fair_area == 0)
+            raise ZeroDivisionError("float division by zero")
         h = set_hash(primer_seqs)
         r = self.db.execute('SELECT "_id" FROM "set" WHERE "_hash" = ?', (h,)).fetchone()
         if r is not None:

@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-REF_DATA = "/root/reference/swga/tests/data"       # build container only; never on the GPU box
+REF_DATA = os.path.join(GOLDEN, "ref")             # copies of the reference's swga/tests/data fixtures
 
 
 def pytest_configure(config):

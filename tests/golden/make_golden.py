@@ -7,6 +7,7 @@ Run in the build container (needs /root/reference and oracle/_ref/{dsk,set_finde
     python tests/golden/make_golden.py
 
 Outputs (committed):
+  edge_q.fq                hand-made FASTQ / mixed quirk file (Bank.cpp:173-201)
   edge_a.fa                hand-made mode-A quirk file (N runs, IUPAC, lower case, CRLF, blank
                            lines, empty / short records, no trailing newline)
   dsk_golden.json          per case and k: distinct, sum, md5[:12] of the sorted "KMER COUNT"
@@ -31,7 +32,7 @@ sys.path.insert(0, ROOT)
 from oracle import swga_oracle as O          # noqa: E402
 from swga_b200 import synth                  # noqa: E402
 
-REF_DATA = "/root/reference/swga/tests/data"
+REF_DATA = os.path.join(HERE, "ref")         # copied from /root/reference/swga/tests/data (test vectors)
 
 EDGE_A = (
     b">r1 multi-line record with N runs > and @ inside the header\r\n"
@@ -49,6 +50,47 @@ EDGE_A = (
     b"ACGTACGTACGTACGTAATTAATTGGCCGGCCGCGCGCGCATATATAT\n"
     b">r6 no trailing newline\n"
     b"GATTACAGATTACAGATTACANGATTACA"
+)
+
+
+# FASTQ and mixed input (Bank.cpp:173-201): 4-line records, CRLF, quality lines that start with '@' / contain '>',
+# multi-line reads whose quality is cut short by a long header comment (dummy still holds the rest of the header
+# line), a FASTA record in between, left-over quality that contains '@' and is then taken for a header, no final
+# newline.
+EDGE_Q = (
+    b"@r1 some comment\n"
+    b"ACGTACGTNNACGTTGCAAC\n"
+    b"+\n"
+    b"IIIIIIIIIIIIIIIIIIII\n"
+    b"@r2\r\n"
+    b"ACGTTGCATGCA\r\n"
+    b"+r2\r\n"
+    b"@@@@>>>>++++\r\n"
+    b"@r3 x\n"
+    b"ACGTACGTAC\n"
+    b"GGGTTTAAAC\n"
+    b"+\n"
+    b"IIIIIIIIII\n"
+    b"IIIIIIIIII\n"
+    b">fa1 fasta record inside\n"
+    b"ACGTNNNNACGTACGTAGCTAGCTAGCTAG\n"
+    b"\n"
+    b"acgtnRYKM\n"
+    b"@r4 long comment so that dummy is long already\n"
+    b"ACGTAC\n"
+    b"+\n"
+    b"II>III\n"
+    b"@r6 0123456789\n"
+    b"ACGTACGTAC\n"
+    b"GGGTTTAAAC\n"
+    b"+\n"
+    b"IIIIIIIIII\n"
+    b"III@IIIIII\n"
+    b"GATTACAGATTACA\n"
+    b"@r5\n"
+    b"TTTTTTTTGGGGGGGGCCCCCCCCAAAAAAAA\n"
+    b"+\n"
+    b"!!!!!!!!!!!!!!!!!!!!!!!!!!!!!!!!"
 )
 
 
@@ -100,12 +142,19 @@ def dsk_counts(fp, k, tmp):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
     gold = {}
+    if only:                                   # regenerate some cases, keep the others as they are
+        with open(os.path.join(HERE, "dsk_golden.json")) as f:
+            gold = json.load(f)
     with tempfile.TemporaryDirectory() as tmp:
         cases = {}
         with open(os.path.join(HERE, "edge_a.fa"), "wb") as f:
             f.write(EDGE_A)
         cases["edge_a"] = (os.path.join(HERE, "edge_a.fa"), [3, 4, 5, 8, 12], [3, 4, 5, 8, 12])
+        with open(os.path.join(HERE, "edge_q.fq"), "wb") as f:
+            f.write(EDGE_Q)
+        cases["edge_q"] = (os.path.join(HERE, "edge_q.fq"), [3, 4, 5, 8, 12], [3, 4, 5, 8, 12])
         for name, fn in RECIPES.items():
             seq, rs = fn()
             fp = os.path.join(tmp, name + ".fa")
@@ -115,6 +164,8 @@ def main():
                    "simple_fg_genome.fa"):
             cases["ref:" + fn] = (os.path.join(REF_DATA, fn), [4] + list(range(5, 13)), [4, 5])
         for name, (fp, ks, full_ks) in cases.items():
+            if only and name not in only:
+                continue
             gold[name] = {}
             for k in ks:
                 d = dsk_counts(fp, k, tmp)
@@ -125,6 +176,8 @@ def main():
                 print(name, k, e["distinct"], e["sum"], e["md5"], flush=True)
     with open(os.path.join(HERE, "dsk_golden.json"), "w") as f:
         json.dump(gold, f, indent=0, sort_keys=True)
+    if only:
+        return
 
     # set_finder: the graph of swga/tests/test_find_sets_cmd.py:35-48 and its expected line
     graph = ("p sp 6 7\n" "n 1 1\nn 2 2\nn 3 1\nn 4 4\nn 5 5\nn 6 6\n"

@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
-REF_DATA = "/root/reference/swga/tests/data"
+REF_DATA = os.path.join(GOLDEN, "ref")      # the reference's own swga/tests/data fixtures, committed as test vectors
 
 _spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
 make_golden = importlib.util.module_from_spec(_spec)
@@ -31,10 +31,13 @@ def table_dict(table, k):
 
 
 def golden_case_bytes(name):
-    """FASTA image of a golden case; None when the case needs /root/reference and it is absent."""
+    """FASTA image of a golden case ("ref:<file>" = a fixture of the reference's swga/tests/data, kept under
+    tests/golden/ref/ so that it also runs on the GPU box)."""
     from swga_b200 import synth
     if name == "edge_a":
         return open(os.path.join(GOLDEN, "edge_a.fa"), "rb").read()
+    if name == "edge_q":
+        return open(os.path.join(GOLDEN, "edge_q.fq"), "rb").read()
     if name in make_golden.RECIPES:
         import tempfile
         seq, rs = make_golden.RECIPES[name]()

@@ -65,14 +65,16 @@ def test_fasta_reader_matches_oracle_reader(lib, oracle):
     from helpers import golden_case_bytes
     extra = [b"", b">a", b">a\n", b">a\r\nAC\r\n\r\nGT\r\n", b">a b c\nACGT\n@q\nTT\n>z\n\n\nAC", b">x\n\rACGT\n",
              b">x\nAC\xffGT\n\xffhdr\nAAA\n", b">only\nA\r\n"]
-    for data in [golden_case_bytes("edge_a"), golden_case_bytes("synth_mode_a")] + extra:
+    fastq = [b"@r1\nACGT\n+\nIIII\n", b"@r1 c\nACGT\n+r1\nIIII", b"@r1\nACGT\n+", b"@r1\nAC\nGT\n+\n@@\n>>\n@r2\nTT\n+\nII\n",
+             b">f\nACGT\n+\nII\nIIXX@h\nGG\n", b"@a 0123456789\nACGTACGTAC\n+\nI\r\n\r\n\n>x\nAC\n", b"@\n+\n\n@b\nA\r\n+\nI"]
+    for data in [golden_case_bytes("edge_a"), golden_case_bytes("edge_q"), golden_case_bytes("synth_mode_a")] + extra + fastq:
         g = fasta.parse_fasta_bytes(data)
         seq, rs = oracle.fasta_parse_dsk(data)
         assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs), data[:40]
     with pytest.raises(Exception):
         fasta.parse_fasta_bytes(b"not fasta\n>x\nACGT\n")         # DSK reads this as a list of file names
-    with pytest.raises(Exception):
-        fasta.parse_fasta_bytes(b"@r1\nACGT\n+\nIIII\n")          # FASTQ is not supported
+    g = fasta.parse_fasta_bytes(b"@r1 x\nACGT\n+\nIIII\n@r2\nGG\n+\n@I\n")       # FASTQ, Bank.cpp:192-201
+    assert g.names == ["r1", "r2"] and bytes(g.seq) == b"ACGTGG"
     g = fasta.parse_fasta_bytes(b"> record1 desc\nAC\n>r2\tx\nGT\n")
     assert g.names == ["record1", "r2"]
 
@@ -88,6 +90,14 @@ def test_threaded_fasta_reader_equals_oracle_reader(lib, oracle, monkeypatch):
     for it in range(300):
         body = b"".join(pieces[i] for i in rng.randint(0, len(pieces), int(rng.randint(0, 40))))
         data = b">first\n" + body
+        g = fasta.parse_fasta_bytes(data)
+        seq, rs = oracle.fasta_parse_dsk(data)
+        assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs), (it, data)
+    # FASTQ records ('+' at a line start) anywhere in the image: the byte-level reader takes over
+    qpieces = pieces + [b"+\n", b"+c\r\n", b"II@I\n", b"I>II\r\n", b"@q some words\n", b"IIIIIIII\n"]
+    for it in range(400):
+        body = b"".join(qpieces[i] for i in rng.randint(0, len(qpieces), int(rng.randint(0, 40))))
+        data = (b">first\n", b"@first c\n")[it & 1] + body
         g = fasta.parse_fasta_bytes(data)
         seq, rs = oracle.fasta_parse_dsk(data)
         assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs), (it, data)

@@ -52,7 +52,9 @@ def test_commands_end_to_end(ws_dir, oracle):
         commands.count(db_name=db, min_size=6, max_size=6)               # would delete rows: needs force
 
     # ---- filter: the active set, locations and Gini of the primers that reached that step
-    active = commands.filter(db_name=db, max_primers=30, min_fg_bind=15, max_bg_bind=200, max_gini=0.85)
+    from swga_b200 import melting
+    active = commands.filter(db_name=db, max_primers=30, min_fg_bind=15, max_bg_bind=200, max_gini=0.85,
+                             min_tm=-20, max_tm=60)
     assert 4 < len(active) <= 30
     recs = oracle.fasta_records_pyfaidx(fgd)
     ends = oracle.chromosome_ends(recs)
@@ -60,6 +62,7 @@ def test_commands_end_to_end(ws_dir, oracle):
         act = ws.primers('"active" = 1')
         assert sorted(p.seq for p in act) == sorted(active)
         for p in act:
+            assert p.tm == melting.temp(p.seq) and -20 <= p.tm <= 60     # filter_tm_range always runs (primers.py:151-165)
             loc = oracle.binding_sites(p.seq, recs)
             assert p.locations == loc
             assert p.gini == oracle.gini(oracle.seq_diff(oracle.linearize_binding_sites([loc], ends)))

@@ -7,7 +7,15 @@ from helpers import golden_case_bytes, table_digest
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["edge_a", "synth_mode_a", "synth_mode_b"]
+# "ref:<file>" = the reference's own swga/tests/data fixtures (copies under tests/golden/ref/), whose real-DSK
+# answers are in dsk_golden.json: bburgdorferi_wgs.fa has IUPAC letters and two 'N' (mode A)
+REF_CASES = ["ref:test.fasta", "ref:bburgdorferi_1k.fa", "ref:ecoli_2k.fa", "ref:bburgdorferi_wgs.fa",
+             "ref:simple_fg_genome.fa"]
+CASES = ["edge_a", "edge_q", "synth_mode_a", "synth_mode_b"] + REF_CASES
+
+
+def k_range(case):
+    return (3, 12) if case in ("edge_a", "edge_q") else (4, 12) if case.startswith("ref:") else (5, 12)
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +36,7 @@ def test_host_call_matches_oracle_and_real_dsk(case, oracle, dsk_golden, torch_c
     g = fasta.parse_fasta_bytes(data)
     seq, rs = oracle.fasta_parse_dsk(data)
     assert np.array_equal(g.seq, seq) and np.array_equal(g.rec_starts, rs)
-    kmin, kmax = (3, 12) if case == "edge_a" else (5, 12)
+    kmin, kmax = k_range(case)
     tabs = kmers.count_all(g, kmin, kmax)
     for k in range(kmin, kmax + 1):
         want = oracle.count_dense(seq, rs, k)
@@ -240,7 +248,7 @@ def test_file_image_call_matches_real_dsk(case, oracle, dsk_golden, torch_cuda, 
     fp = tmp_path / "g.fa"
     fp.write_bytes(data)
     seq, rs = oracle.fasta_parse_dsk(data)
-    kmin, kmax = (3, 12) if case == "edge_a" else (5, 12)
+    kmin, kmax = k_range(case)
     tabs = _file_tables(fp, kmin, kmax)
     g = fasta.parse_fasta_bytes(data)
     assert (tabs.n_bases, tabs.n_records, tabs.mode_b) == (len(seq), len(rs) - 1, g.dsk_mode_b)
@@ -284,6 +292,25 @@ def test_file_image_chunking(oracle, torch_cuda, tmp_path, monkeypatch):
                 assert np.array_equal(out, want), (chunk, stream, i, mode_b, data[:60])
 
 
+def test_file_image_fastq_record_deep_inside_fasta(oracle, torch_cuda, tmp_path, monkeypatch):
+    """A FASTQ record ('+' at a line start) far behind the head of a '>' file: the line-parallel reader has already
+    counted chunks when it meets it; swga_count_fasta_host starts over with the byte-level reader."""
+    from swga_b200 import kmers, synth
+    monkeypatch.setenv("SWGA_FASTA_CHUNK", "4096")
+    monkeypatch.setenv("SWGA_STREAM_CHUNK", "65536")
+    seq = synth.bases(12, 0, 400_000, 0.4)
+    fp = str(tmp_path / "mixed.fa")
+    synth.write_fasta(fp, seq, np.array([0, 150_000, 400_000], dtype=np.uint64))
+    with open(fp, "ab") as f:
+        f.write(b"@q1 x\nACGTTGCAACGTTGCAGGA\n+\n@II>IIIIIIIIIIIIIII\n>tail\nGATTACAGATTACAGATTACA\n")
+    data = open(fp, "rb").read()
+    want_seq, want_rs = oracle.fasta_parse_dsk(data)
+    assert len(want_rs) - 1 == 4 and len(want_seq) == 400_000 + 19 + 21
+    got = kmers.count_all(fp, 5, 12)
+    assert (got.n_bases, got.n_records, got.mode_b) == (len(want_seq), 4, False)
+    assert np.array_equal(got.block, oracle.count_dense_allk(want_seq, want_rs, 5, 12, mode_b=0))
+
+
 def test_file_image_large_multi_chunk(oracle, torch_cuda, tmp_path):
     """Default range / chunk sizes on a file of several chunks (200 Mbp, 5 records, mode B): equal to the
     host-buffer call on the parsed genome (which the partitioned-kernel tests tie to the oracle)."""
@@ -317,9 +344,9 @@ def test_file_image_gzip_and_errors(oracle, torch_cuda, tmp_path):
     (tmp_path / "bad.fa").write_bytes(b"not fasta\n>x\nACGT\n")
     with pytest.raises(_lib.SwgaError, match="not a FASTA image"):
         kmers.count_all(str(tmp_path / "bad.fa"), 5, 9)
-    (tmp_path / "q.fq").write_bytes(b"@r1\nACGT\n+\nIIII\n")
-    with pytest.raises(_lib.SwgaError, match="FASTQ"):
-        kmers.count_all(str(tmp_path / "q.fq"), 5, 9)
+    (tmp_path / "q.fq").write_bytes(b"@r1\nACGTACGTAC\n+\nIIIIIIIIII\n")                 # FASTQ is read (Bank.cpp:192-201)
+    q = kmers.count_all(str(tmp_path / "q.fq"), 5, 9)
+    assert (q.n_bases, q.n_records) == (10, 1) and int(q.table(5).sum()) == 6
     (tmp_path / "empty.fa").write_bytes(b"")
     e = kmers.count_all(str(tmp_path / "empty.fa"), 5, 9)
     assert e.n_bases == 0 and not e.block.any()
@@ -346,3 +373,122 @@ def test_file_image_mode_choice_at_the_10001_record_limit(n_small, big_len, want
     a = kmers.count_all(str(tmp_path / "m.fa"), 5, 8)
     assert a.mode_b == want_b and (a.n_bases, a.n_records) == (g.n_bases, g.n_records)
     assert np.array_equal(a.block, kmers.count_all(g, 5, 8).block)
+
+
+# ---- the counting seam itself: swga.kmers.count_kmers(k, genome_fp, cwd, threshold) (swga/kmers.py:23-56) ----
+
+@pytest.mark.parametrize("case", CASES)
+def test_count_kmers_seam_fresh_path(case, oracle, dsk_golden, torch_cuda, tmp_path, monkeypatch):
+    """The fresh path of the seam -- GPU count -> swga_write_dsk_file -> _parse_kmer_binary -- into an EMPTY cwd:
+    the returned dict equals the real DSK's counts (golden) and the oracle's, the written file is a DSK result
+    file (re-read by the restated reference parser, swga/kmers.py:94-115), the threshold is applied both in the
+    file and in the dict, a second call parses the cache file without counting (kmers.py:34-40), and a failure
+    removes the partial file and re-raises (kmers.py:45-50)."""
+    from swga_b200 import kmers
+    data = golden_case_bytes(case)
+    fp = tmp_path / (case.replace("ref:", "") + ".fa")
+    fp.write_bytes(data)
+    cwd = tmp_path / "swga_tmp"
+    cwd.mkdir()
+    seq, rs = oracle.fasta_parse_dsk(data)
+    for ks, gold in sorted(dsk_golden[case].items(), key=lambda kv: int(kv[0])):
+        k = int(ks)
+        kmers._TABLE_CACHE.clear()
+        got = kmers.count_kmers(k, str(fp), str(cwd), 1)
+        want_tab = oracle.count_dense(seq, rs, k)
+        want = {oracle.code_to_kmer(c, k): int(want_tab[c]) for c in np.nonzero(want_tab)[0]}
+        assert got == want, (case, k)
+        assert len(got) == gold["distinct"] and sum(got.values()) == gold["sum"]
+        if "counts" in gold:
+            assert got == gold["counts"]                           # the real dsk's answer, record for record
+        out = cwd / ("%s-%dmers.solid_kmers_binary" % (fp.name, k))
+        assert out.is_file()
+        assert out.stat().st_size == 8 + 12 * len(got)             # [i32 64][i32 k]([u64 code][u32 count])*
+        assert dict(oracle.parse_kmer_binary(str(out))) == got
+    # threshold (-t): the file holds only counts >= threshold and so does the dict
+    k = 5
+    for thr in (2, 3):
+        cw = tmp_path / ("thr%d" % thr)
+        cw.mkdir()
+        got = kmers.count_kmers(k, str(fp), str(cw), thr)
+        t = oracle.count_dense(seq, rs, k)
+        want = {oracle.code_to_kmer(c, k): int(t[c]) for c in np.nonzero(t >= thr)[0]}
+        assert got == want
+        assert dict(oracle.parse_kmer_binary(str(cw / ("%s-%dmers.solid_kmers_binary" % (fp.name, k))))) == want
+    # second call: the cache file is parsed, nothing is counted; the threshold is re-applied on top of it
+    def boom(*a, **kw):
+        raise AssertionError("count_kmers recounted although the cache file exists")
+    with monkeypatch.context() as m:
+        m.setattr(kmers, "_tables_for", boom)
+        again = kmers.count_kmers(5, str(fp), str(cwd), 1)
+        t = oracle.count_dense(seq, rs, 5)
+        assert again == {oracle.code_to_kmer(c, 5): int(t[c]) for c in np.nonzero(t)[0]}
+        assert kmers.count_kmers(5, str(fp), str(cwd), 4) == {a: b for a, b in again.items() if b >= 4}
+    # failure: the partial file is removed and the exception re-raised
+    class Boom(Exception):
+        pass
+    cw = tmp_path / "fail"
+    cw.mkdir()
+    partial = cw / ("%s-5mers.solid_kmers_binary" % fp.name)
+
+    def fail_after_partial_write(genome_fp, k_):
+        partial.write_bytes(b"\x40\x00\x00\x00")
+        raise Boom()
+    with monkeypatch.context() as m:
+        m.setattr(kmers, "_tables_for", fail_after_partial_write)
+        with pytest.raises(Boom):
+            kmers.count_kmers(5, str(fp), str(cw), 1)
+    assert not list(cw.iterdir())
+
+
+def test_count_kmers_seam_bad_genome(torch_cuda, tmp_path):
+    """swga/kmers.py:45-50: when the counter fails (here: the file is not FASTA) nothing is left in cwd."""
+    from swga_b200 import _lib, kmers
+    (tmp_path / "bad.fa").write_bytes(b"not fasta\n")
+    cwd = tmp_path / "t"
+    cwd.mkdir()
+    with pytest.raises(_lib.SwgaError):
+        kmers.count_kmers(5, str(tmp_path / "bad.fa"), str(cwd), 1)
+    assert not list(cwd.iterdir())
+    with pytest.raises(AssertionError):
+        kmers.count_kmers(5, str(tmp_path / "bad.fa"), str(cwd), 1.0)      # kmers.py:32 threshold must be int
+
+
+def test_full_size_c2_background_vs_oracle(oracle, torch_cuda):
+    """BASELINE.md 4.6 / SURVEY 8(d): the 3.1 Gbp background of configs C2 / C3 (24 records, DSK mode B), counted once
+    on the device exactly as bench.py's step does, against the CPU oracle on EVERY table k = 5..12, bit for bit.
+    The oracle counts the 24 records on the host cores in parallel (same C function, per-record tables summed).
+    The bases the oracle reads are the device generator's, copied back; slices of them are compared with the
+    host generator (swga_b200.synth) so that both sides provably count the SURVEY 8(d) genome."""
+    import time
+    torch = torch_cuda
+    from swga_b200 import _lib, kmers, synth
+    lib, ctx = _lib.load(), _lib.context(0)
+    seed, n, gc, n_rec = synth.CONFIGS["C2_bg"]
+    assert synth.CONFIGS["C3_bg"] == synth.CONFIGS["C2_bg"]
+    ta, tc, tg = synth.thresholds(gc)
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.swga_synth_bases(ctx.h, seed, 0, n, ta, tc, tg, _lib.ptr(d), None))
+    rs = synth.equal_records(n, n_rec)
+    fwd, canon = kmers.count_all_device(d, rs, mode_b=True)
+    torch.cuda.synchronize()
+    stats = np.zeros(4, dtype=np.uint64)
+    _lib.check(lib.swga_count_partition_stats(ctx.h, stats.ctypes.data_as(_lib.c_u64p)))
+    got = u32(canon)
+    del fwd, canon
+    seq = np.empty(n, dtype=np.uint8)
+    step = 1 << 28
+    for o in range(0, n, step):
+        seq[o:o + step] = d[o:o + step].cpu().numpy()
+    del d
+    torch.cuda.empty_cache()
+    for o in (0, 1_234_567_890, 2 ** 31 - 500_000, 2 ** 31 + 7, n - 1_000_000):
+        assert np.array_equal(seq[o:o + 1_000_000], synth.bases(seed, o, min(1_000_000, n - o), gc)), o
+    t0 = time.time()
+    want = oracle.count_dense_allk_parallel(seq, rs, 5, 12, mode_b=1)
+    dt = time.time() - t0
+    bad = int(np.count_nonzero(got != want))
+    print("3.1 Gbp oracle: %.1f s on %d host threads; partition exits %s; mismatching slots %d" % (
+        dt, __import__("os").cpu_count(), stats.tolist(), bad))
+    assert bad == 0
+    assert int(got[-4 ** 12:].astype(np.int64).sum()) == int(np.maximum(0, np.diff(rs.astype(np.int64)) - 11).sum())

@@ -85,3 +85,57 @@ def test_native_set_line_parser_equals_read_set_finder_line():
         assert [int(x) for x in ids[i] if x >= 0] == want_ids and w[i] == want_w
     ids2, w2, ok2, c2 = score.parse_set_lines(b"1,2,3,4 1.0\n", 3)          # more ids than max_m: flagged
     assert not ok2[0] and c2 == 12
+
+
+def test_default_score_set_with_duplicated_locations(oracle):
+    """The reference's default_score_set takes ANY list of locations: stats.seq_diff keeps the zero gaps of
+    repeated positions (stats.py:22-33).  linearize_binding_sites never produces such a list, so the case is
+    evaluated on the host (swga_b200/score.py) -- against the restated stats.py."""
+    for locs in ([1, 3, 3, 5, 7, 7, 7, 20], [5, 5, 9, 100, 100, 101], [0, 0, 1, 2], [10, 4, 4, 30, 10]):
+        for expr in ("fg_dist_mean * fg_dist_gini / bg_dist_mean", "fg_dist_std + set_size + fg_max_dist"):
+            want_score, want_ns = oracle.default_score_set(expr, [1, 2, 3], list(locs), 13, 2.5)
+            got_score, got_ns = score.default_score_set(expr, [1, 2, 3], list(locs), 13, 2.5)
+            assert got_ns["fg_dist_mean"] == want_ns["fg_dist_mean"]
+            assert got_ns["fg_dist_gini"] == want_ns["fg_dist_gini"]
+            assert got_ns["fg_dist_std"] == pytest.approx(want_ns["fg_dist_std"], rel=1e-12)
+            assert got_score == pytest.approx(want_score, rel=1e-12)
+    with pytest.raises(ZeroDivisionError):
+        score.default_score_set("fg_dist_mean", [1], [4, 4, 4], 0, 1.0)          # all gaps 0: fair_area == 0
+
+
+def test_melting_temperature_restatement():
+    """swga_b200/melting.py (parity unpinned: the reference's `melt` package is not vendored).  Sanity of the
+    nearest-neighbour model: GC raises Tm, length raises Tm, the value is strand-symmetric for a palindrome,
+    swga's default window (15..45 C, filter.yaml) selects 8..12-mers of ordinary composition."""
+    from swga_b200 import melting
+    assert melting.temp("GGGCCCGG") > melting.temp("ACGTACGT") > melting.temp("AAAATTTT")
+    assert melting.temp("ACGTACGTACGT") > melting.temp("ACGTACGT")
+    assert melting.temp("aaaatttt") == melting.temp("AAAATTTT")
+    assert 15 < melting.temp("AAAATTTT") < 45 and 15 < melting.temp("GATTACAGATTA") < 45
+    assert abs(melting.temp("ACGTACGT") - melting.temp("ACGTACGT", uncorrected=True)) < 5
+    with pytest.raises(ValueError):
+        melting.temp("ACGN")
+
+
+def test_filter_skip_filtering_activates_every_listed_primer(tmp_path, capsys):
+    """Primers.activate(self.max_primers) (swga/primers.py:275-290, commands/filter.py:42): max_primers is only the
+    number below which the 'Fewer than' note is printed -- every primer of the list is marked active."""
+    from swga_b200 import commands, workspace
+    db = str(tmp_path / "swga.db")
+    w = workspace.Workspace(db)
+    w.create_tables()
+    w.metadata = dict(version=workspace.VERSION, fg_file="fg.fa", bg_file="bg.fa", ex_file=None, fg_length=100000,
+                      bg_length=2000000)
+    seqs = ["AAGT", "AACC", "AGGA", "CCTG", "GATT", "TTGC"]
+    w.add_primers([dict(seq=s, fg_freq=5, bg_freq=1, ratio=5.0) for s in seqs], add_revcomp=False)
+    w.close()
+    lst = tmp_path / "primers.txt"
+    lst.write_text("".join(s + "\n" for s in seqs[:5]))
+    act = commands.filter(db_name=db, input=str(lst), skip_filtering=True, max_primers=3)
+    assert sorted(act) == sorted(seqs[:5])
+    assert "Fewer than" not in capsys.readouterr().err
+    act = commands.filter(db_name=db, input=str(lst), skip_filtering=True, max_primers=10)
+    assert sorted(act) == sorted(seqs[:5])
+    assert "Fewer than 10 primers were selected (5 passed all the filters)" in capsys.readouterr().err
+    with workspace.connection(db) as w:
+        assert sorted(p.seq for p in w.primers('"active" = 1')) == sorted(seqs[:5])

@@ -7,7 +7,7 @@ import pytest
 
 from helpers import golden_case_bytes, table_digest, table_dict
 
-CASES = ["edge_a", "synth_mode_a", "synth_mode_b", "ref:test.fasta", "ref:bburgdorferi_1k.fa",
+CASES = ["edge_a", "edge_q", "synth_mode_a", "synth_mode_b", "ref:test.fasta", "ref:bburgdorferi_1k.fa",
          "ref:ecoli_2k.fa", "ref:bburgdorferi_wgs.fa", "ref:simple_fg_genome.fa"]
 
 
