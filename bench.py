@@ -2,12 +2,16 @@
 """bench.py -- headline benchmark of the swga hot path on B200.
 
 Metric (BASELINE.json): Gbases/s of all-k (k = 5..12) both-strand counting.  One "step" = one pass of
-the counting path over the workload: pack + mark + accumulate (+ NCCL allreduce at N > 1) + finalize +
-fold for the foreground AND the background genome, producing the canonical tables of both.
+the counting path over the workload: pack + mark + accumulate (+ the cross-GPU merge at N > 1) + finalize +
+fold for the foreground AND the background genome, producing the canonical tables of both on every GPU.
 
 Workload at every N: BASELINE.json configs[1] (= C2): synthetic 4.4 Mbp GC-rich foreground, 3.1 Gbp
 human-sized background (SURVEY.md 8d generator).  At N > 1 the background is sharded by contiguous
-chunk with an 11-base halo (strong scaling: total work fixed), the foreground is replicated.
+chunk with an 11-base halo (strong scaling: total work fixed), the foreground is replicated.  The same
+step on BASELINE configs[2] (C3: 23 Mbp AT-rich foreground) is timed as the per-N extra `c3`.
+
+The second half of BASELINE.json's metric -- candidate sets scored per second (configs[3], C4) -- is the
+`scoring` object of the same line: sets sharded by set index over the ranks, no collective.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
@@ -30,6 +34,7 @@ sys.path.insert(0, ROOT)
 KMIN, KMAX = 5, 12
 METRIC = "allk_count_throughput"
 UNIT = "Gbases/s"
+CPU_SAMPLE_DEFAULT = 10_000_000          # = the C1 background: DSK's ~1 s per invocation is < 10 % of a run
 
 
 def parse_args():
@@ -40,10 +45,20 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
     ap.add_argument("--bg-bases", type=float, default=None, help="override background size (debug only)")
-    ap.add_argument("--cpu-sample-bases", type=int, default=600_000)
+    ap.add_argument("--cpu-sample-bases", type=int, default=None,
+                    help="bases of the background prefix the CPU arm counts per step (default: 10 Mbp in the "
+                         "reference arm, 5 Mbp in the cpu_baseline leg of the b200 arm)")
+    ap.add_argument("--cpu-budget-s", type=float, default=1200.0,
+                    help="reference arm: shrink the sample so that all timed steps fit this many seconds")
+    ap.add_argument("--score-sets", type=float, default=1e7, help="candidate sets of the 'typical' scoring workload")
+    ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--verify-full", action="store_true",
+                    help="also compare every table of the full-size background with the CPU oracle (the checker) "
+                         "counted on the host cores in parallel; result in full_size_properties.oracle_equal")
     return ap.parse_args()
 
 
@@ -73,12 +88,12 @@ def cpu_reference_pass(workload, sample_bases, parallel):
         if have_dsk:
             fa = os.path.join(tmp, "sample.fa")
             synth.write_fasta(fa, seq, synth.equal_records(sample, 1))
-            jobs = [(fa, k, tmp) for k in range(KMIN, KMAX + 1)]
+            jobs = [(fa, k, tmp) for k in range(KMAX, KMIN - 1, -1)]         # longest job first
             t0 = time.perf_counter()
             if parallel > 1:
                 import multiprocessing as mp
                 with mp.get_context("fork").Pool(parallel) as pool:
-                    pool.map(_dsk_one, jobs)
+                    pool.map(_dsk_one, jobs, chunksize=1)
             else:
                 for j in jobs:
                     _dsk_one(j)
@@ -90,26 +105,53 @@ def cpu_reference_pass(workload, sample_bases, parallel):
         return time.perf_counter() - t0, sample, "port", 1
 
 
+def cpu_full_runs():
+    """Full C1 / C5 runs of the reference path (tools/cpu_full_runs.py, tens of minutes, measured once)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cpu_full_runs.json")) as f:
+            d = json.load(f)
+        return {"source": "profiles/r02_cpu_full_runs.json (tools/cpu_full_runs.py; host %s, %s cpus; dsk k=5..12 one after "
+                          "another on 1 core + record parser, full genomes)" % (d.get("host"), d.get("cpus")),
+                "runs": {c: {k: v for k, v in r.items() if k != "per_run"} for c, r in d.get("runs", {}).items()}}
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = min(KMAX - KMIN + 1, os.cpu_count() or 1)
+    want = args.cpu_sample_bases or CPU_SAMPLE_DEFAULT
+    # Warm-up steps run a 1 Mbp sample (they only warm the page cache and the binary); the first one also sizes the
+    # timed sample: DSK costs ~1 s per invocation plus a part linear in the bases, and all timed steps have to fit
+    # --cpu-budget-s (the default 10 Mbp sample is kept when it does).
+    t_small = None
+    for _ in range(args.warmup):
+        dt, b, _, _ = cpu_reference_pass(args.workload, min(want, 1_000_000), cores)
+        t_small = dt if t_small is None else min(t_small, dt)
+    sample = want
+    if t_small is not None and want > 1_000_000:
+        per_mbp = max(t_small - 1.0, 0.05 * t_small)
+        predicted = 1.0 + per_mbp * want / 1e6
+        if predicted * args.steps > args.cpu_budget_s:
+            sample = int(max(2_000_000, min(want, (args.cpu_budget_s / args.steps - 1.0) / per_mbp * 1e6)))
     vals = []
-    for i in range(args.warmup + args.steps):
-        dt, bases, kind, used = cpu_reference_pass(args.workload, args.cpu_sample_bases, cores)
-        if i >= args.warmup:
-            vals.append(dt)
+    for _ in range(args.steps):
+        dt, bases, kind, used = cpu_reference_pass(args.workload, sample, cores)
+        vals.append(dt)
     ms = 1e3 * sum(vals) / len(vals)
     value = bases / (ms * 1e-3) / 1e9
-    sample = ("%d-base prefix of the %s background, dsk k=5..12 as %d concurrent processes (the reference runs "
-              "them one after another on one core) + Python record parser" % (bases, args.workload, used))
+    desc = ("%d-base prefix of the %s background per step, dsk k=5..12 as %d concurrent processes (the reference runs "
+            "them one after another on one core) + Python record parser; warm-up steps use 1 Mbp"
+            % (bases, args.workload, used))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "sample_bases": bases},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": desc,
+                         "full_runs": cpu_full_runs()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,6 +268,14 @@ def bind_to_gpu_numa_node(index):
         return None
 
 
+def load_json(*parts):
+    try:
+        with open(os.path.join(ROOT, *parts)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -257,71 +307,8 @@ def run_b200_arm(args):
             os.close(saved)
     lib, ctx = _lib.load(), _lib.context(local)
     P = _lib.ptr
-
-    fg_seed, n_fg, fg_gc, fg_nrec = synth.CONFIGS[args.workload + "_fg"]
-    bg_seed, n_bg, bg_gc, bg_nrec = synth.CONFIGS[args.workload + "_bg"]
-    if args.bg_bases:
-        n_bg = int(args.bg_bases)
     words = int(lib.swga_tables_words(KMIN, KMAX))
-
-    class Dev(object):
-        """one genome (or one rank's shard of it) resident in HBM"""
-
-        def __init__(self, seed, n_total, gc, n_rec, shard):
-            rs = synth.equal_records(n_total, n_rec)
-            a, b = dist.shard_bounds(n_total, rank, world) if shard else (0, n_total)
-            e = min(n_total, b + KMAX - 1)
-            self.n, self.n_starts, self.a = e - a, b - a, a
-            self.mode_b = bool(np.diff(rs.astype(np.int64))[:10001].max() > 1000000)
-            inner = rs[(rs > a) & (rs < e)] - np.uint64(a)
-            self.rs = np.concatenate([[0], inner, [e - a]]).astype(np.uint64)
-            ta, tc, tg = synth.thresholds(gc)
-            self.ascii = torch.empty(max(self.n, 16), dtype=torch.uint8, device=dev)
-            _lib.check(lib.swga_synth_bases(ctx.h, seed, a, self.n, ta, tc, tg, P(self.ascii), None))
-            self.d_rs = torch.from_numpy(self.rs.view(np.int64).copy()).to(dev)
-            self.packed = torch.empty(int(lib.swga_packed_words(self.n)), dtype=torch.int32, device=dev)
-            self.brk = torch.empty(int(lib.swga_brk_words(self.n)), dtype=torch.int32, device=dev)
-            self.fwd = torch.empty(words, dtype=torch.int32, device=dev)
-            self.canon = torch.empty(words, dtype=torch.int32, device=dev)
-            self.launches = 0
-
-        def accumulate(self, ev=None):
-            """zero + pack + mark + swga_count_accumulate: this rank's additive table block"""
-            self.fwd.zero_()
-            _lib.check(lib.swga_pack(ctx.h, P(self.ascii), self.n, 0 if self.mode_b else 1, P(self.packed), P(self.brk), None))
-            k = 1
-            if len(self.rs) > 2:
-                _lib.check(lib.swga_mark_records(ctx.h, P(self.d_rs[1:]), len(self.rs) - 2, self.n, P(self.brk), None))
-                k += 1
-            if ev is not None:
-                ev[0].record()
-            _lib.check(lib.swga_count_accumulate(ctx.h, P(self.packed), P(self.brk), self.n_starts, KMIN, KMAX, P(self.fwd), None))
-            if ev is not None:
-                ev[1].record()
-            # accumulate = k_bucket_hist (sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count
-            # when the partitioned path applies (>= 14 Mi starts, kmax 11 or 12), else the single k_count
-            acc = 5 if (self.n_starts >= (14 << 20) and 8 <= 2 * KMAX - 14 <= 10) else 1
-            # + k_marginalize per level + k_fold (k < 10) + k_fold_tiled per k >= 10
-            self.launches = k + acc + (KMAX - KMIN) + (1 if KMIN < 10 else 0) + max(0, KMAX - max(KMIN, 10) + 1)
-
-        def finish(self):
-            """finalize + fold of the (allreduced) block"""
-            _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
-            _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
-
-    fg = Dev(fg_seed, n_fg, fg_gc, fg_nrec, shard=False)
-    bg = Dev(bg_seed, n_bg, bg_gc, bg_nrec, shard=True)
-    torch.cuda.synchronize()
-
-    def step(ev=None):
-        # the background's allreduce (NCCL, its own stream) runs while this rank counts the replicated foreground
-        bg.accumulate(ev)
-        work = td.all_reduce(bg.fwd, op=td.ReduceOp.SUM, async_op=True) if world > 1 else None
-        fg.accumulate()
-        fg.finish()
-        if work is not None:
-            work.wait()
-        bg.finish()
+    merge = dist.TableMerge(words, KMIN, KMAX, dev) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -329,33 +316,109 @@ def run_b200_arm(args):
             td.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    def rank_max(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    class Dev(object):
+        """one genome (or one rank's shard of it) resident in HBM"""
+
+        def __init__(self, seed, n_total, gc, n_rec, shard, ascii_t=None, rs=None):
+            rs = synth.equal_records(n_total, n_rec) if rs is None else rs
+            a, b = dist.shard_bounds(n_total, rank, world) if shard else (0, n_total)
+            e = min(n_total, b + KMAX - 1)
+            self.n, self.n_starts, self.a = e - a, b - a, a
+            self.mode_b = bool(np.diff(rs.astype(np.int64))[:10001].max() > 1000000)
+            inner = rs[(rs > a) & (rs < e)] - np.uint64(a)
+            self.rs = np.concatenate([[0], inner, [e - a]]).astype(np.uint64)
+            if ascii_t is None:
+                ta, tc, tg = synth.thresholds(gc)
+                self.ascii = torch.empty(max(self.n, 16), dtype=torch.uint8, device=dev)
+                _lib.check(lib.swga_synth_bases(ctx.h, seed, a, self.n, ta, tc, tg, P(self.ascii), None))
+            else:
+                self.ascii = ascii_t[a:e]
+            self.d_rs = torch.from_numpy(self.rs.view(np.int64).copy()).to(dev)
+            self.packed = torch.empty(int(lib.swga_packed_words(self.n)), dtype=torch.int32, device=dev)
+            self.brk = torch.empty(int(lib.swga_brk_words(self.n)), dtype=torch.int32, device=dev)
+            self.fwd = merge.block() if (shard and merge is not None) else torch.empty(words, dtype=torch.int32, device=dev)
+            self.canon = torch.empty(words, dtype=torch.int32, device=dev)
+
+        def accumulate(self, ev=None):
+            """zero + pack + mark + swga_count_accumulate: this rank's additive table block"""
+            _lib.check(lib.swga_memset(ctx.h, P(self.fwd), 0, words * 4, None))
+            _lib.check(lib.swga_pack(ctx.h, P(self.ascii), self.n, 0 if self.mode_b else 1, P(self.packed), P(self.brk), None))
+            if len(self.rs) > 2:
+                _lib.check(lib.swga_mark_records(ctx.h, P(self.d_rs[1:]), len(self.rs) - 2, self.n, P(self.brk), None))
+            if ev is not None:
+                ev[0].record()
+            _lib.check(lib.swga_count_accumulate(ctx.h, P(self.packed), P(self.brk), self.n_starts, KMIN, KMAX, P(self.fwd), None))
+            if ev is not None:
+                ev[1].record()
+
+        def finish(self):
+            """finalize + fold of the (merged) block"""
+            _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(self.fwd), None))
+            _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(self.fwd), P(self.canon), None))
+
+    def make_step(fg, bg):
+        def step(ev=None, mev=None):
+            # the background's cross-GPU merge runs while this rank counts the replicated foreground
+            bg.accumulate(ev)
+            if merge is not None:
+                merge.start(bg.fwd, mev)
+            fg.accumulate()
+            fg.finish()
+            if merge is not None:
+                merge.finish(bg.fwd, bg.canon, mev)           # leaves the finalized forward block and the canonical block
+            else:
+                bg.finish()
+        return step
+
+    def time_steps(step, n_steps, n_warm):
+        for _ in range(n_warm):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        mev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_steps)] if merge is not None else None
+        barrier()
+        l0 = int(lib.swga_launch_count())
+        e0.record()
+        for i in range(n_steps):
+            step(kev[i], mev[i] if mev else None)
+        e1.record()
+        barrier()
+        launches = int(lib.swga_launch_count()) - l0
+        total_ms = e0.elapsed_time(e1)
+        count_ms = sum(a.elapsed_time(b) for a, b in kev) / n_steps
+        merge_ms = (sum(a.elapsed_time(b) for a, b in mev) / n_steps) if mev else 0.0
+        total_ms, count_ms, merge_ms = rank_max([total_ms, count_ms, merge_ms])
+        return total_ms / n_steps, count_ms, merge_ms, launches
+
+    fg_seed, n_fg, fg_gc, fg_nrec = synth.CONFIGS[args.workload + "_fg"]
+    bg_seed, n_bg, bg_gc, bg_nrec = synth.CONFIGS[args.workload + "_bg"]
+    if args.bg_bases:
+        n_bg = int(args.bg_bases)
+    fg = Dev(fg_seed, n_fg, fg_gc, fg_nrec, shard=False)
+    bg = Dev(bg_seed, n_bg, bg_gc, bg_nrec, shard=True)
+    torch.cuda.synchronize()
+    step = make_step(fg, bg)
+
+    n_warm = max(3, args.warmup)
+    for _ in range(n_warm):
         step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(kev[i])
-    e1.record()
-    barrier()
+    ms_per_step, count_ms, merge_ms, launches = time_steps(step, args.steps, 0)
     sampler.stop_flag = True
-    total_ms = e0.elapsed_time(e1)
-    count_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    t = torch.tensor([total_ms, count_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    total_ms, count_ms = float(t[0]), float(t[1])
-    ms_per_step = total_ms / args.steps
     value = (n_fg + n_bg) / (ms_per_step * 1e-3) / 1e9
     sampler.join(timeout=2)
     clocks = sampler.summary()
 
     # ---- per-kernel times of the count stage: CUDA events recorded inside swga_count_accumulate, on its stream ----
-    part_ms = hist_ms = bcount_ms = None
     _lib.check(lib.swga_ctx_set_stage_timing(ctx.h, 1))
     acc = [0.0, 0.0, 0.0]
     n_st = max(3, min(args.steps, 10))
@@ -367,97 +430,101 @@ def run_b200_arm(args):
             acc[i] += st[i] / n_st
     _lib.check(lib.swga_ctx_set_stage_timing(ctx.h, 0))
     torch.cuda.synchronize()
-    t = torch.tensor(acc, dtype=torch.float64, device=dev)
-    if world > 1:
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-    hist_ms, part_ms, bcount_ms = (float(x) for x in t)
+    hist_ms, part_ms, bcount_ms = rank_max(acc)
     partitioned = part_ms > 0
 
+    # ---- shared-memory operation peak (the ceiling the count stage runs against) and the L2 red peak ----
+    ms = ctypes.c_float()
+    _lib.check(lib.swga_bench_atom_shared(ctx.h, 1 << 14, 1 << 33, ctypes.byref(ms)))
+    sh_peak = (1 << 33) / (ms.value * 1e-3) / 1e9            # G random 4-byte shared atomics / s, 64 KB table
+    red_peak = None
+    if rank == 0 and not args.no_extras:
+        tab = torch.zeros(1 << 24, dtype=torch.int32, device=dev)
+        _lib.check(lib.swga_bench_red_global(ctx.h, P(tab), 1 << 24, 1 << 31, ctypes.byref(ms)))
+        red_peak = (1 << 31) / (ms.value * 1e-3) / 1e9
+        del tab
+
     # ---- roofline of the dominant kernel on this rank's background shard ----
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    tr = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_count_stage_traffic.json")) as f:
-            tr = json.load(f)
-    except Exception:
-        pass
+    peaks = load_json("MEASURED_PEAKS.json")
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs") if "hbm_gbs" in peaks else (
+        6650.0, "fallback of B200_PROFILING.md")
+    tr = load_json("profiles", "r02_count_stage_traffic.json") or load_json("profiles", "r01_count_stage_traffic.json")
     if partitioned:
-        # k_partition reads the packed genome once: 1/4 B per base (+ 1/32 B of break mask); the 2-byte bucket
-        # elements it writes are this implementation's own intermediate, counted under `traffic`, not here
+        # k_partition reads the packed genome once: 1/4 B per base (+ 1/32 B of break mask); the bucket elements it
+        # writes are this implementation's own intermediate, counted under `traffic`, not here
         k_bytes = (0.25 + 1.0 / 32.0) * bg.n_starts
         k_ms, k_name = part_ms, "k_partition"
         k_traffic = tr.get("k_partition_dram_bytes_per_base")
+        smem_ops = 0.5                                        # slot atomics per base: one per element = per two bases
     else:
         k_bytes = (0.25 + 1.0 / 32.0) * bg.n_starts + 4.0 * 4 ** KMAX
         k_ms, k_name = count_ms, "k_count"
-        k_traffic = None
+        k_traffic, smem_ops = None, 0.0
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
     stage_bytes = 0.25 * bg.n_starts + 4.0 * 4 ** KMAX         # packed genome read once + top table written once
-    roofline = {"kernel": k_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": k_traffic * bg.n_starts if k_traffic else None,
-                "peak_source": peak_src, "ms_per_launch": k_ms, "share_of_step": k_ms / ms_per_step,
-                "dram_gbs_actual": (k_traffic * bg.n_starts / (k_ms * 1e-3) / 1e9) if k_traffic else None,
-                "count_stage": {"kernels": "k_bucket_hist(sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count"
-                                if partitioned else "k_count",
-                                "ms": count_ms, "share_of_step": count_ms / ms_per_step,
-                                "ms_hist_layout": hist_ms, "ms_partition": part_ms, "ms_bucket_count": bcount_ms,
-                                "bytes_alg": stage_bytes, "achieved": stage_bytes / (count_ms * 1e-3) / 1e9,
-                                "frac": stage_bytes / (count_ms * 1e-3) / 1e9 / hbm_peak,
-                                "traffic": tr.get("dram_bytes_per_base", 0) * bg.n_starts or None},
-                "note": "k_partition is bound by the L1/shared-memory data pipe (ncu: l1tex data-pipe wavefronts 77-85 % of peak, "
-                        "DRAM 21 %), not by HBM: every element costs one shared atomic and one 2-byte shared store with "
-                        "~3.8-way bank serialisation; see 'atomic' and profiles/r01_summary.md"}
+    stage_ops = 1.0                                            # shared atomics per base, whole stage: slot + histogram bin per element
+    roofline = {
+        "kernel": k_name, "bound": "smem" if partitioned else "l2_atomic",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": k_traffic * bg.n_starts if k_traffic else None, "peak_source": peak_src,
+        "ms_per_launch": k_ms, "share_of_step": k_ms / ms_per_step,
+        "dram_gbs_actual": (k_traffic * bg.n_starts / (k_ms * 1e-3) / 1e9) if k_traffic else None,
+        # the ceiling this kernel runs against: random shared-memory atomics (one slot atomic per element in k_partition,
+        # one bin atomic per element in k_bucket_count; an element = two bases) against the live microbenchmark
+        "smem_atomics_per_base": smem_ops,
+        "smem_gops": smem_ops * bg.n_starts / (k_ms * 1e-3) / 1e9 if partitioned else None,
+        "smem_peak_gops": sh_peak,
+        "smem_frac": (smem_ops * bg.n_starts / (k_ms * 1e-3) / 1e9 / sh_peak) if partitioned else None,
+        "count_stage": {
+            "kernels": "k_bucket_hist(sample) + k_bucket_layout + k_partition + k_item_prefix + k_bucket_count"
+                       if partitioned else "k_count",
+            "ms": count_ms, "share_of_step": count_ms / ms_per_step, "ms_hist_layout": hist_ms,
+            "ms_partition": part_ms, "ms_bucket_count": bcount_ms, "bytes_alg": stage_bytes,
+            "achieved": stage_bytes / (count_ms * 1e-3) / 1e9,
+            "frac": stage_bytes / (count_ms * 1e-3) / 1e9 / hbm_peak,
+            "traffic": tr.get("dram_bytes_per_base", 0) * bg.n_starts or None,
+            "updates_per_s_g": bg.n_starts / (count_ms * 1e-3) / 1e9,
+            "smem_frac": stage_ops * bg.n_starts / (count_ms * 1e-3) / 1e9 / sh_peak if partitioned else None,
+            "red_global_64MB_peak_gops": red_peak},
+        "note": "k_partition is bound by the L1/shared-memory data pipe (ncu: l1tex data-pipe wavefronts, DRAM ~20 %), not by "
+                "HBM: `frac` is the algorithmic HBM fraction the contract asks for, `smem_frac` the fraction of the ceiling "
+                "the kernel actually runs against; see profiles/r02_summary.md"}
     path_bytes = 1.5 * (fg.n + bg.n) + 2 * 2 * 4.0 * words       # 1.5 B/base + 2T per genome
     path = {"bytes_alg": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s"}
     path["frac"] = path["achieved"] / hbm_peak
 
-    # ---- A_peak: random red.global.add.u32 on a 64 MB table; shared atomics on a 64 KB table ----
-    atomic = None
-    if rank == 0 and not args.no_extras:
-        ms = ctypes.c_float()
-        tab = torch.zeros(1 << 24, dtype=torch.int32, device=dev)
-        _lib.check(lib.swga_bench_red_global(ctx.h, P(tab), 1 << 24, 1 << 31, ctypes.byref(ms)))
-        red_peak = (1 << 31) / (ms.value * 1e-3) / 1e9
-        _lib.check(lib.swga_bench_atom_shared(ctx.h, 1 << 14, 1 << 33, ctypes.byref(ms)))
-        sh_peak = (1 << 33) / (ms.value * 1e-3) / 1e9
-        ach = bg.n_starts / (count_ms * 1e-3) / 1e9
-        atomic = {"achieved_gops": ach, "red_global_64MB_peak_gops": red_peak, "frac": ach / red_peak,
-                  "atom_shared_64KB_peak_gops": sh_peak, "ops_alg_per_base": 1,
-                  "note": "1 table update per base (top table k=12 + tails; k<12 by marginalisation). The partitioned "
-                          "path spends 2 shared-memory atomics/base (staging slot in k_partition, bin in k_bucket_count) "
-                          "instead of 1 L2 red/base"}
-        del tab
-
     # ---- e2e: host buffers through the C-ABI host calls, H2D + D2H inside the timed region ------
+    # The result is wanted on ONE host: rank 0 counts the (replicated) foreground and copies both canonical blocks
+    # back; the other ranks stream their background shard and take part in the merge.
     e2e = None
     if not args.no_e2e:
-        h_fg = torch.empty(fg.n, dtype=torch.uint8, pin_memory=True)
         h_bg = torch.empty(bg.n, dtype=torch.uint8, pin_memory=True)
-        h_fg.copy_(fg.ascii[:fg.n])
         h_bg.copy_(bg.ascii[:bg.n])
-        h_canon_fg = torch.empty(words, dtype=torch.int32, pin_memory=True)
-        h_canon_bg = torch.empty(words, dtype=torch.int32, pin_memory=True)
         cs = torch.cuda.ExternalStream(lib.swga_ctx_compute_stream(ctx.h), device=dev)
-        fg_rs, bg_rs = np.ascontiguousarray(fg.rs), np.ascontiguousarray(bg.rs)
+        bg_rs = np.ascontiguousarray(bg.rs)
+        if rank == 0:
+            h_fg = torch.empty(fg.n, dtype=torch.uint8, pin_memory=True)
+            h_fg.copy_(fg.ascii[:fg.n])
+            h_canon_fg = torch.empty(words, dtype=torch.int32, pin_memory=True)
+            h_canon_bg = torch.empty(words, dtype=torch.int32, pin_memory=True)
+            fg_rs = np.ascontiguousarray(fg.rs)
 
         def e2e_step():
-            _lib.check(lib.swga_count_genome_host(ctx.h, P(h_fg), fg.n, P(fg_rs), len(fg_rs) - 1, int(fg.mode_b),
-                                                  KMIN, KMAX, P(h_canon_fg)))
+            if rank == 0:
+                _lib.check(lib.swga_count_genome_host(ctx.h, P(h_fg), fg.n, P(fg_rs), len(fg_rs) - 1, int(fg.mode_b),
+                                                      KMIN, KMAX, P(h_canon_fg)))
             with torch.cuda.stream(cs):
-                bg.fwd.zero_()
+                _lib.check(lib.swga_memset(ctx.h, P(bg.fwd), 0, words * 4, cs.cuda_stream))
                 _lib.check(lib.swga_count_stream_host(ctx.h, P(h_bg), bg.n, P(bg_rs), len(bg_rs) - 1, int(bg.mode_b),
                                                       KMIN, KMAX, bg.n_starts, P(bg.fwd)))
-                if world > 1:
-                    td.all_reduce(bg.fwd, op=td.ReduceOp.SUM)
-                _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(bg.fwd), cs.cuda_stream))
-                _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(bg.fwd), P(bg.canon), cs.cuda_stream))
-                h_canon_bg.copy_(bg.canon, non_blocking=True)
+                if merge is not None:
+                    merge.start(bg.fwd, None)
+                    merge.finish(bg.fwd, bg.canon, None)
+                else:
+                    _lib.check(lib.swga_count_finalize(ctx.h, KMIN, KMAX, P(bg.fwd), cs.cuda_stream))
+                    _lib.check(lib.swga_fold_canonical(ctx.h, KMIN, KMAX, P(bg.fwd), P(bg.canon), cs.cuda_stream))
+                if rank == 0:
+                    h_canon_bg.copy_(bg.canon, non_blocking=True)
             cs.synchronize()
 
         n_e2e = max(3, min(args.steps, 5))
@@ -468,18 +535,26 @@ def run_b200_arm(args):
         for _ in range(n_e2e):
             e2e_step()
         barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        dt = rank_max([(time.perf_counter() - t0) / n_e2e])[0]
+        t = torch.tensor([float(bg.n + 8 * len(bg_rs))], dtype=torch.float64, device=dev)
         if world > 1:
-            td.all_reduce(dt, op=td.ReduceOp.MAX)
-        e2e = {"value": (n_fg + n_bg) / float(dt[0]) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(fg.n + bg.n + 8 * (len(fg_rs) + len(bg_rs))),
-               "d2h_bytes_per_step": int(2 * 4 * words), "ms_per_step": float(dt[0]) * 1e3, "steps": n_e2e,
-               "api": "swga_count_genome_host / swga_count_stream_host (pinned host buffers)"}
-        # parity of the two paths on the full-size workload: a checksum of the tables
-        same = bool(torch.equal(h_canon_bg.to(dev), bg.canon))
-        e2e["tables_equal_device_path"] = same
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+        h2d_total = int(t[0]) + int(fg.n + 8 * len(fg.rs))
+        if rank == 0:
+            e2e = {"value": (n_fg + n_bg) / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
+                   "d2h_bytes_per_step": int(2 * 4 * words), "ms_per_step": dt * 1e3, "steps": n_e2e,
+                   "h2d_gbs_aggregate": h2d_total / dt / 1e9,
+                   "api": "swga_count_genome_host / swga_count_stream_host (pinned host buffers); results to rank 0's host",
+                   "tables_equal_device_path": None}
+        # parity of the two paths on the full-size workload
+        step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            e2e["tables_equal_device_path"] = bool(torch.equal(h_canon_bg.to(dev), bg.canon))
+            del h_fg, h_canon_fg, h_canon_bg
+        del h_bg
 
-    # ---- size-independent parity properties of the full-size tables (no CPU oracle at 3.1 Gbp) ----
+    # ---- size-independent parity properties of the full-size tables, and the oracle itself on request ----
     props = None
     if world == 1 and not args.no_extras:
         step()
@@ -495,10 +570,22 @@ def run_b200_arm(args):
                 up = bg.fwd[o1:o1 + 4 ** (k + 1)].view(-1, 4).sum(1, dtype=torch.int64)
                 diff = bg.fwd[o0:o1].to(torch.int64) - up
                 ok &= bool((diff >= 0).all()) and int(diff.sum()) == bg_nrec
-        props = {"bg_tables_sum_and_marginals_ok": bool(ok)}
+        props = {"bg_tables_sum_and_marginals_ok": bool(ok),
+                 "oracle_equal": "see GPU test test_full_size_c2_background_vs_oracle (every table of the 3.1 Gbp background "
+                                 "against the CPU oracle); --verify-full repeats it here"}
+        if args.verify_full:
+            from oracle import swga_oracle as O                 # the checker
+            seq = np.empty(bg.n, dtype=np.uint8)
+            for o in range(0, bg.n, 1 << 28):
+                seq[o:o + (1 << 28)] = bg.ascii[o:o + (1 << 28)].cpu().numpy()
+            t0 = time.perf_counter()
+            want = O.count_dense_allk_parallel(seq, synth.equal_records(n_bg, bg_nrec), KMIN, KMAX, mode_b=int(bg.mode_b))
+            props["oracle_equal"] = bool(np.array_equal(bg.canon.cpu().numpy().view(np.uint32), want))
+            props["oracle_s"] = time.perf_counter() - t0
+            del seq, want
 
     # ---- the count -> primer-row merge of `swga count` on the tables just built (BASELINE config 2: count + filter) ----
-    merge = None
+    count_merge = None
     if rank == 0 and not args.no_extras:
         cap = 1 << 22
         rows = torch.empty(cap * 4, dtype=torch.int32, device=dev)
@@ -513,103 +600,258 @@ def run_b200_arm(args):
                                                P(rows), cap, P(n_rows), None))
             f1.record()
             torch.cuda.synchronize()
-            ms = f0.elapsed_time(f1)
-            best = ms if best is None else min(best, ms)
-        merge = {"kernel": "k_filter_primers", "ms": best, "rows": int(n_rows.item()), "min_fg_bind": min_fg,
-                 "max_bg_bind": max_bg, "max_dimer_bp": 3, "codes_tested": int(words)}
+            ms_ = f0.elapsed_time(f1)
+            best = ms_ if best is None else min(best, ms_)
+        count_merge = {"kernel": "k_filter_primers", "ms": best, "rows": int(n_rows.item()), "min_fg_bind": min_fg,
+                       "max_bg_bind": max_bg, "max_dimer_bp": 3, "codes_tested": int(words)}
         del rows
 
-    scoring = None
-    if rank == 0 and not args.no_extras:
+    # ---- BASELINE configs[2]: the same step with the 23 Mbp AT-rich foreground (partitioned path on every rank) ----
+    c3 = None
+    if not args.no_extras and args.workload == "C2" and not args.bg_bases:
+        s3, n3, g3, r3 = synth.CONFIGS["C3_fg"]
+        fg3 = Dev(s3, n3, g3, r3, shard=False)
+        ms3, cnt3, mrg3, _ = time_steps(make_step(fg3, bg), max(3, min(args.steps, 10)), 2)
+        c3 = {"workload": workload_name("C3"), "ms_per_step": ms3, "value": (n3 + n_bg) / (ms3 * 1e-3) / 1e9, "unit": UNIT,
+              "bg_count_stage_ms": cnt3, "merge_ms": mrg3}
+        del fg3
+
+    # ---- low-entropy input: a genome built to make the sampled bucket layout wrong (N = 1 only) ----
+    hostile = None
+    if world == 1 and not args.no_extras and not args.bg_bases:
         try:
-            scoring = scoring_extra(dev)
+            hostile = hostile_extra(dev, lib, ctx, Dev, time_steps, fg)
+        except Exception as e:
+            hostile = {"error": repr(e)}
+
+    del bg.ascii, bg.packed, bg.brk
+    torch.cuda.empty_cache()
+
+    scoring = None
+    if not args.no_extras and not args.no_scoring:
+        try:
+            scoring = scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak)
         except Exception as e:                      # the counting line must survive a failure of the extra
+            import traceback
+            traceback.print_exc()
             scoring = {"error": repr(e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        dt, bases, kind, cores = cpu_reference_pass(args.workload, args.cpu_sample_bases, 1)
+        cores = min(KMAX - KMIN + 1, os.cpu_count() or 1)
+        dt, bases, kind, cores = cpu_reference_pass(args.workload, args.cpu_sample_bases or 5_000_000, cores)
         cpu = {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": "%d-base prefix of the background: dsk k=5..12 run one after another (as "
-                         "swga/commands/count.py:84-91 does) + record parser; %.1f s" % (bases, dt)}
+               "sample": "%d-base prefix of the background: the reference's dsk binary for k=5..12 as %d concurrent processes "
+                         "(swga/commands/count.py:84-91 runs them one after another on one core) + the record parser of "
+                         "swga/kmers.py:94-115; %.1f s" % (bases, cores, dt),
+               "full_runs": cpu_full_runs()}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "fg_bases": n_fg, "bg_bases": n_bg,
                        "kmin": KMIN, "kmax": KMAX, "sharding": "bg contiguous chunks + 11-base halo, fg replicated"
                        if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
-            "roofline": roofline, "path_roofline": path, "atomic": atomic, "cpu_baseline": cpu, "e2e": e2e,
-            "clocks": clocks, "gpu_launches": (fg.launches + bg.launches) * args.steps, "numa_node": numa,
-            "scoring": scoring, "count_merge": merge, "full_size_properties": props,
+            "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": clocks, "gpu_launches": launches, "numa_node": numa,
+            "merge": {"impl": merge.name, "exposed_ms": merge_ms} if merge is not None else None,
+            "scoring": scoring, "c3": c3, "low_entropy": hostile, "count_merge": count_merge,
+            "full_size_properties": props,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        td.barrier()
         td.destroy_process_group()
 
 
-def scoring_extra(dev):
-    """Second headline of BASELINE.json: candidate sets scored per second on one B200 (kernel (d)), device
-    resident site lists and sets, CUDA events.  Workload C4 of SURVEY.md 8(d) on a 2x10^5-set sample of the
-    10^7 (the 200 most frequent 8..12-mers of the 23 Mbp AT-rich foreground: ~2x10^5 unique sites per
-    set), plus a 'typical' variant with 200 12-mers of ~400 sites each (the scale of swga's default
-    min_fg_bind = 1e-5 * fg_length), 10^6 sets."""
+def hostile_extra(dev, lib, ctx, Dev, time_steps, fg):
+    """No throughput cliff when the sample is wrong: the genome of tests/test_count_gpu.py::
+    test_partitioned_kernel_on_hostile_composition scaled to 1.2 Gbp -- composition drifting along the genome
+    (gc 0.15 / 0.80 / 0.45 thirds), a 15 Mbp dinucleotide repeat, a 10 Mbp poly-A run, 7.5 Mbp of N (mode B: N -> G),
+    and a 14-base-period repeat over 30 % of the genome placed only where the sampler does not look."""
     import numpy as np
     import torch
-    from swga_b200 import fasta, kmers, locate, score, synth, workloads
+    from swga_b200 import _lib, synth
+    P = _lib.ptr
+    n = 1_200_000_000
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    third = n // 3
+    for i, (seed, gc) in enumerate(((51, 0.15), (52, 0.80), (53, 0.45))):
+        lo = i * third
+        m = third if i < 2 else n - 2 * third
+        ta, tc, tg = synth.thresholds(gc)
+        _lib.check(lib.swga_synth_bases(ctx.h, seed, 0, m, ta, tc, tg, P(a[lo:lo + m]), None))
+    ac = torch.tensor([65, 67], dtype=torch.uint8, device=dev).repeat(7_500_000)
+    a[100_000_000:115_000_000] = ac
+    a[250_000_000:260_000_000] = 65
+    a[450_000_000:457_500_000] = 78
+    unit = torch.from_numpy(np.frombuffer(b"ACGTTGCAAGGCTT" * 1200, dtype=np.uint8).copy()).to(dev)
+    stride = min(64, max(1, ((n + 31) // 32) >> 15))
+    for lo in range(800_000_000, 1_160_000_000, 1 << 26):
+        hi = min(1_160_000_000, lo + (1 << 26))
+        pos = torch.arange(lo, hi, device=dev)
+        hidden = (pos % (1024 * stride)) >= 1100
+        seg = a[lo:hi]
+        seg[hidden] = unit[pos[hidden] % unit.numel()]
+    rs = synth.equal_records(n, 10)
+    g = Dev(0, n, 0.0, 10, shard=False, ascii_t=a, rs=rs)
+
+    def step(ev=None, mev=None):
+        g.accumulate(ev)
+        g.finish()
+    ms, cnt, _, _ = time_steps(step, 5, 2)
+    stats = np.zeros(4, dtype=np.uint64)
+    _lib.check(lib.swga_count_partition_stats(ctx.h, stats.ctypes.data_as(_lib.c_u64p)))
+    lens = np.diff(rs.astype(np.int64))
+    o12 = int(lib.swga_table_offset(KMIN, KMAX))
+    ok = int(g.canon[o12:].sum(dtype=torch.int64)) == int(np.maximum(0, lens - KMAX + 1).sum())
+    return {"bases": n, "ms_per_step": ms, "value": n / (ms * 1e-3) / 1e9, "unit": UNIT, "count_stage_ms": cnt,
+            "partition_exits": {"staging_full": int(stats[0]), "bucket_full": int(stats[1]), "uniform_groups": int(stats[2]),
+                                "break_groups": int(stats[3])},
+            "top_table_sum_ok": bool(ok),
+            "composition": "gc 0.15 / 0.80 / 0.45 thirds, 15 Mbp (AC)n, 10 Mbp poly-A, 7.5 Mbp N, 14-periodic repeat hidden from "
+                           "the sampler over 30 % of the genome; 10 records (mode B)"}
+
+
+def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
+    """Second half of BASELINE.json's metric: candidate sets scored per second (kernel (d)); device-resident site
+    lists and sets, CUDA events, best of 3; sets sharded by set index over the ranks (score.shard_sets), no
+    collective.  Workloads on the 23 Mbp AT-rich foreground (configs[3]):
+      C4_dense  SURVEY 8(d)'s C4 primers: the 200 most frequent 8..12-mers (~2 x 10^5 unique sites per set)
+      typical   200 12-mers of ~400 sites each (the scale of swga's default min_fg_bind = 1e-5 * fg_length)
+    each with the default max_fg_bind_dist = 36000 and with no early reject (every set needs Gini)."""
+    import numpy as np
+    import torch
+    from swga_b200 import _lib, fasta, kmers, locate, score, synth, workloads
+    lib, ctx = _lib.load(), _lib.context(dev.index)
+    P = _lib.ptr
     seed, n, gc, n_rec = synth.CONFIGS["C3_fg"]
-    g = fasta.Genome(synth.bases(seed, 0, n, gc), synth.equal_records(n, n_rec), ["chr%d" % (i + 1) for i in range(n_rec)])
+    names = ["chr%d" % (i + 1) for i in range(n_rec)]
+    g = fasta.Genome(synth.bases(seed, 0, n, gc), synth.equal_records(n, n_rec), names)
     tabs = kmers.count_all(g, 5, 12)
-    gi = locate.GenomeIndex(g)
-    out = {"unit": "sets/s", "fg_bases": n, "timing": "CUDA events, best of 3, device-resident inputs; e2e = host API (numpy in, numpy out), wall clock, best of 3"}
+    out = {"unit": "sets/s", "fg_bases": n, "n_gpus": world,
+           "timing": "CUDA events, best of 3, device-resident site lists and set array; sets sharded by set index, slowest "
+                     "rank counts; e2e = host API (numpy set array + bg_dist_mean in, numpy results out), wall clock"}
     t12 = tabs.table(12)
     order = np.argsort(-t12.astype(np.int64), kind="stable")
     lo = int(np.searchsorted(-t12[order].astype(np.int64), -400))
+    c4 = workloads.top_primers(tabs, 5, 12, 200)
+    c4_seqs = [kmers.codes_to_kmers([c], k)[0] for k, c, _ in c4]
+
+    # ---- locate: CSR index build + both-strand locate + strand union of the 200 C4 primers ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gi = locate.GenomeIndex(g)
+    sl_dense = score.SiteLists.from_index(gi, c4_seqs)
+    torch.cuda.synchronize()
+    t_loc = time.perf_counter() - t0
+    loc = {"primers": len(c4_seqs), "k_values": sorted({len(s) for s in c4_seqs}), "seconds": t_loc,
+           "primers_per_s": len(c4_seqs) / t_loc, "sites_located": int(sl_dense.counts()[:-1].sum()),
+           "includes": "H2D of the 23 Mbp genome, strict pack, one CSR index per k, locate of both strands, strand union, "
+                       "tile offsets (wall clock, one pass, cold)"}
     variants = {
-        "C4_dense": ([kmers.codes_to_kmers([c], k)[0] for k, c, _ in workloads.top_primers(tabs, 5, 12, 200)], 200_000),
-        "typical_400_sites": (kmers.codes_to_kmers(order[lo:lo + 200], 12), 1_000_000),
+        "C4_dense": (c4_seqs, int(args.score_sets_dense), sl_dense),
+        "typical_400_sites": (kmers.codes_to_kmers(order[lo:lo + 200], 12), int(args.score_sets), None),
     }
-    for name, (seqs, S) in variants.items():
-        sl = score.SiteLists.from_index(gi, seqs)
-        sets_, _ = workloads.c4_sets(S)
-        mapped = np.where(sets_ >= 0, sl.list_of_primer[np.clip(sets_, 0, 199)], -1).astype(np.int32)
-        mapped_host = sets_
-        d_sets = torch.from_numpy(mapped).to(dev)
-        bg = torch.full((S,), 1000.0, dtype=torch.float64, device=dev)
-        row = {"sets": S}
+    recs = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import swga_oracle as O                   # cpu_baseline leg: the restated reference, timed
+        recs = [(names[r], bytes(g.seq[int(g.rec_starts[r]):int(g.rec_starts[r + 1])]).decode("ascii")) for r in range(n_rec)]
+        t0 = time.perf_counter()
+        n_cpu = 24
+        for s_ in c4_seqs[:n_cpu]:
+            O.binding_sites(s_, recs)
+        dt = time.perf_counter() - t0
+        loc["cpu_baseline"] = {"value": n_cpu / dt, "unit": "primers/s", "cores": 1, "kind": "port",
+                               "sample": "restated locate.binding_sites (swga/locate.py:39-51,76-90) for the first %d of the 200 "
+                                         "C4 primers on the 23 Mbp foreground, %.1f s; 200 primers extrapolated: %.0f s"
+                                         % (n_cpu, dt, dt / n_cpu * 200)}
+    out["locate"] = loc
+
+    for name, (seqs, S, sl) in variants.items():
+        if sl is None:
+            sl = score.SiteLists.from_index(gi, seqs)
+        lo_s, hi_s = score.shard_sets(S, rank, world)
+        S_r = hi_s - lo_s
+        d_raw = torch.empty((max(S_r, 1), 10), dtype=torch.int32, device=dev)
+        _lib.check(lib.swga_synth_sets(ctx.h, 8, lo_s, S_r, 200, P(d_raw), None))
+        d_raw = d_raw[:S_r]
+        lop = torch.from_numpy(np.ascontiguousarray(sl.list_of_primer, dtype=np.int32)).to(dev)
+        d_sets = torch.where(d_raw >= 0, lop[d_raw.clamp(0, 199).long()], d_raw.new_full((), -1))
+        bg = torch.full((S_r,), 1000.0, dtype=torch.float64, device=dev)
+        # algorithmic bytes per set (SURVEY 8d): 4 (sum of the set's site lists + 2R) + 4 m + 8 + 41
+        cnt = torch.from_numpy(sl.counts().astype(np.int64)).to(dev)
+        n_bounds = int(cnt[-1])
+        m = (d_raw >= 0).sum(1)
+        l_raw = torch.where(d_sets >= 0, cnt[d_sets.clamp(0).long()], torch.zeros((), dtype=torch.int64, device=dev)).sum(1) + n_bounds
+        bytes_alg = float((4 * l_raw + 4 * m + 49).sum())
+        merged = float(l_raw.sum())
+        row = {"sets": S, "sets_this_rank": S_r, "mean_raw_sites_per_set": merged / max(S_r, 1)}
         for label, max_fg in (("max_fg_36000", 36000), ("no_reject", 2 ** 31 - 1)):
             best = None
             for _ in range(3):
+                barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 res = score.score_sets(sl, None, bg, max_fg, d_sets=d_sets, return_device=True)
                 e1.record()
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1)
+                ms = rank_max([e0.elapsed_time(e1)])[0]
                 best = ms if best is None else min(best, ms)
-            L = res.n_sites.cpu().numpy().view(np.uint32)
-            st = res.status.cpu().numpy()
-            # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
-            h_bg = np.full(S, 1000.0)
-            e2e_s = None
-            for _ in range(3):                                   # best of 3, like the device timing above
-                torch.cuda.synchronize()
+            st = res.status
+            L = res.n_sites
+            r = {"sets_per_s": S / best * 1e3, "ms": best,
+                 "mean_unique_sites_per_set": float(L.to(torch.float64).mean()) if S_r else 0.0,
+                 "passed_frac": float((st & 1).to(torch.float64).mean()) if S_r else 0.0,
+                 "merged_sites_per_s": merged / best * 1e3,
+                 "roofline": {"kernel": "k_score_dense" if name == "C4_dense" else "k_score_sort", "bound": "smem",
+                              "bytes_alg_per_set": bytes_alg / max(S_r, 1),
+                              "achieved": bytes_alg / (best * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": bytes_alg / (best * 1e-3) / 1e9 / hbm_peak,
+                              "smem_frac": merged / (best * 1e-3) / 1e9 / sh_peak,
+                              "note": "site lists are L2-resident; smem_frac = merged sites/s against the shared-memory "
+                                      "operation peak (one operation per merged site is the floor)"}}
+            if world == 1:
+                # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
+                h_sets = d_raw.cpu().numpy()
+                h_bg = np.full(S_r, 1000.0)
+                e2e_s = None
+                for _ in range(2):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    hres = score.score_sets(sl, h_sets, h_bg, max_fg)
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    e2e_s = dt if e2e_s is None else min(e2e_s, dt)
+                n_pass = int(hres.passed.sum())
+                d2h = S_r * 5 + n_pass * 44 if (S_r > (1 << 17) and 2 * n_pass <= S_r) else S_r * 41
+                r["e2e"] = {"value": S_r / e2e_s, "unit": "sets/s", "h2d_bytes_per_step": int(h_sets.nbytes + h_bg.nbytes),
+                            "d2h_bytes_per_step": int(d2h)}
+                del h_sets, hres
+            row[label] = r
+        # CPU baseline (BASELINE.md 4.5): the restated score_set on the first sets of the workload, bounded to ~10 s
+        if recs is not None:
+            from oracle import swga_oracle as O
+            ends = O.chromosome_ends(recs)
+            locs = [gi.binding_sites(s_) for s_ in seqs]        # Primer.locations as `swga filter` stored them
+            sets_h, _ = workloads.c4_sets(4000)
+            for label, max_fg in (("max_fg_36000", 36000), ("no_reject", 2 ** 31 - 1)):
                 t0 = time.perf_counter()
-                score.score_sets(sl, sets_, h_bg, max_fg)
-                torch.cuda.synchronize()
+                done = 0
+                for row_ in sets_h:
+                    O.score_set([locs[i] for i in row_ if i >= 0], max_fg, 1000.0, ends)
+                    done += 1
+                    if time.perf_counter() - t0 > 6.0:
+                        break
                 dt = time.perf_counter() - t0
-                e2e_s = dt if e2e_s is None else min(e2e_s, dt)
-            n_pass = int((st & 1).sum())
-            # score.score_sets: bulk calls copy back status + max_dist of every set and the rest for the passing ones
-            d2h = S * 5 + n_pass * 44 if (S > (1 << 17) and 2 * n_pass <= S) else S * 41
-            row[label] = {"sets_per_s": S / best * 1e3, "ms": best, "mean_unique_sites_per_set": float(L.mean()),
-                          "passed_frac": float((st & 1).mean()),
-                          "merged_sites_per_s": float(sl.counts()[:-1].mean()) * 8 * S / best * 1e3,
-                          "e2e_sets_per_s": S / e2e_s, "e2e_h2d_bytes": int(mapped_host.nbytes + h_bg.nbytes),
-                          "e2e_d2h_bytes": int(d2h)}
+                row[label]["cpu_baseline"] = {
+                    "value": done / dt, "unit": "sets/s", "cores": 1, "kind": "port",
+                    "sample": "restated score.score_set + stats (swga/score.py:73-98, stats.py:10-54, Python-2 arithmetic) on the "
+                              "first %d sets, %.1f s; %d sets extrapolated: %.0f s" % (done, dt, S, S / (done / dt))}
         out[name] = row
+        del d_sets, d_raw, bg
     return out
 
 

@@ -274,6 +274,14 @@ int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *
 int swga_synth_bases(swga_ctx *ctx, uint64_t seed, uint64_t start, uint64_t n,
                      uint32_t t_a, uint32_t t_c, uint32_t t_g, uint8_t *d_ascii, void *stream);
 
+/* Candidate sets of workload C4 (bit-identical to swga_b200/workloads.py): n_sets rows of 10
+ * int32 primer indices in [0, n_primers), 6..10 per set, -1 padded, for sets start .. start + n_sets - 1. */
+int swga_synth_sets(swga_ctx *ctx, uint64_t seed, uint64_t start, uint64_t n_sets, uint32_t n_primers,
+                    int32_t *d_sets, void *stream);
+
+/* Kernel launches issued by this library since it was loaded (all contexts; bench.py's gpu_launches). */
+uint64_t swga_launch_count(void);
+
 /* ---- atomic-throughput microbenchmarks (the A_peak of SURVEY.md 8d) ----------------------------
  * Issues n_ops uniformly random red.global.add.u32 on a table of `table_words` words (global) or
  * shared-memory atomics on a per-CTA table of `table_words` words; returns milliseconds. */

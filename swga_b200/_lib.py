@@ -83,6 +83,8 @@ SIGNATURES = {
                                            ctypes.c_uint64, c_f64p, c_vp]),
     "swga_synth_bases": (ctypes.c_int, [c_ctx, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp]),
+    "swga_synth_sets": (ctypes.c_int, [c_ctx, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, c_vp, c_vp]),
+    "swga_launch_count": (ctypes.c_uint64, []),
     "swga_bench_red_global": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_uint64,
                                              ctypes.POINTER(ctypes.c_float)]),
     "swga_bench_atom_shared": (ctypes.c_int, [c_ctx, ctypes.c_uint32, ctypes.c_uint64,

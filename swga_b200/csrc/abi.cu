@@ -25,7 +25,11 @@ void swga_set_error(const char *fmt, ...)
     va_end(ap);
 }
 extern "C" const char *swga_last_error(void) { return g_err; }
-extern "C" int swga_abi_version(void) { return 1; }
+extern "C" int swga_abi_version(void) { return 2; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void swga_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t swga_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---- context --------------------------------------------------------------------------------
 static int ctx_init_streams(swga_ctx *c)

@@ -36,6 +36,10 @@ void swga_set_error(const char *fmt, ...);
         if (_r != SWGA_OK) return _r;                                                    \
     } while (0)
 
+// ---- launch counter (bench.py's gpu_launches): every kernel launch of the library goes through this ----
+void swga_note_launch();
+#define SWGA_NOTE_LAUNCH() swga_note_launch()
+
 // ---- context --------------------------------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;

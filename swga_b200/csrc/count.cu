@@ -238,6 +238,36 @@ k_synth(uint64_t seed, uint64_t start, uint64_t n, uint32_t ta, uint32_t tc, uin
     }
 }
 
+// Candidate sets of workload C4, bit-identical to swga_b200/workloads.py c4_sets: set s has
+// m = 6 + h(base) mod 5 members, base = (seed << 40) + 64 s: the first m distinct values of h(base + t) mod P,
+// t = 1, 2, ... (t < 64); rows of 10 int32, -1 padded.
+__global__ void __launch_bounds__(256)
+k_synth_sets(uint64_t seed, uint64_t start, uint64_t n_sets, uint32_t n_primers, int32_t *__restrict__ out)
+{
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_sets) return;
+    const uint64_t base = (seed << 40) + 64ull * (start + i);
+    const int m = 6 + (int)(splitmix64(base) % 5ull);
+    int32_t row[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) row[j] = -1;
+    int filled = 0;
+    for (uint64_t t = 1; t < 64 && filled < m; ++t) {
+        const int32_t c = (int32_t)(splitmix64(base + t) % (uint64_t)n_primers);
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) dup |= row[j] == c;
+        if (!dup) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+                if (j == filled) row[j] = c;
+            ++filled;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) out[i * 10 + j] = row[j];
+}
+
 // ------------------------------------------------------------------------------------------------
 // atomic-throughput microbenchmarks (A_peak)
 // ------------------------------------------------------------------------------------------------
@@ -324,7 +354,7 @@ extern "C" int swga_pack(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, int 
     ARG_CHECK(mask_mode >= SWGA_MASK_NONE && mask_mode <= SWGA_MASK_STRICT);
     ARG_CHECK((reinterpret_cast<uintptr_t>(d_ascii) & 15) == 0);
     const uint64_t groups = (n + 31) / 32 + 1;                 // one zero pad group after the data
-    k_pack<<<grid_for(groups, 256), 256, 0, as_stream(stream)>>>(d_ascii, n, mask_mode, d_packed, d_brk, groups);
+    SWGA_NOTE_LAUNCH(); k_pack<<<grid_for(groups, 256), 256, 0, as_stream(stream)>>>(d_ascii, n, mask_mode, d_packed, d_brk, groups);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -333,7 +363,7 @@ int swga_mark_records_origin(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64
                              uint64_t n, uint32_t *d_brk, cudaStream_t stream)
 {
     if (n_rec == 0) return SWGA_OK;
-    k_mark_records<<<grid_for(n_rec, 256), 256, 0, stream>>>(d_rec_starts, n_rec, origin, n, d_brk);
+    SWGA_NOTE_LAUNCH(); k_mark_records<<<grid_for(n_rec, 256), 256, 0, stream>>>(d_rec_starts, n_rec, origin, n, d_brk);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -368,7 +398,7 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     }
     ctx->part_stats = nullptr;
     ctx->stage_valid = 0;
-    k_count<<<grid_for((n_starts + 31) / 32, 256), 256, 0, st>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables, offs);
+    SWGA_NOTE_LAUNCH(); k_count<<<grid_for((n_starts + 31) / 32, 256), 256, 0, st>>>(d_packed, d_brk, n_starts, kmin, kmax, d_tables, offs);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -380,7 +410,7 @@ extern "C" int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *
     const TableOffs o = swga_make_offs(kmin, kmax);
     for (int k = kmax - 1; k >= kmin; --k) {
         const uint64_t n_lower = 1ull << (2 * k);
-        k_marginalize<<<grid_for(n_lower, 256), 256, 0, as_stream(stream)>>>(
+        SWGA_NOTE_LAUNCH(); k_marginalize<<<grid_for(n_lower, 256), 256, 0, as_stream(stream)>>>(
             reinterpret_cast<const uint4 *>(d_tables + o.off[k + 1]), d_tables + o.off[k], n_lower);
         CUDA_TRY(cudaGetLastError());
     }
@@ -398,10 +428,11 @@ extern "C" int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint
     if (kmin < k_split) {
         const int k_hi = std::min(kmax, k_split - 1);
         const uint64_t total = swga_tables_words(kmin, k_hi);
-        k_fold<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, k_hi, offs, total);
+        SWGA_NOTE_LAUNCH(); k_fold<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, k_hi, offs, total);
     }
-    for (int k = k_split; k <= kmax; ++k)
-        k_fold_tiled<<<1u << (2 * (k - 6)), 256, 0, as_stream(stream)>>>(d_fwd + offs.off[k], d_canon + offs.off[k], k);
+    for (int k = k_split; k <= kmax; ++k) {
+        SWGA_NOTE_LAUNCH(); k_fold_tiled<<<1u << (2 * (k - 6)), 256, 0, as_stream(stream)>>>(d_fwd + offs.off[k], d_canon + offs.off[k], k);
+    }
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -412,7 +443,17 @@ extern "C" int swga_synth_bases(swga_ctx *ctx, uint64_t seed, uint64_t start, ui
     ARG_CHECK(ctx && (d_ascii || n == 0));
     ARG_CHECK((reinterpret_cast<uintptr_t>(d_ascii) & 15) == 0);
     if (n == 0) return SWGA_OK;
-    k_synth<<<grid_for((n + 15) / 16, 256), 256, 0, as_stream(stream)>>>(seed, start, n, t_a, t_c, t_g, d_ascii);
+    SWGA_NOTE_LAUNCH(); k_synth<<<grid_for((n + 15) / 16, 256), 256, 0, as_stream(stream)>>>(seed, start, n, t_a, t_c, t_g, d_ascii);
+    CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}
+
+extern "C" int swga_synth_sets(swga_ctx *ctx, uint64_t seed, uint64_t start, uint64_t n_sets, uint32_t n_primers,
+                               int32_t *d_sets, void *stream)
+{
+    ARG_CHECK(ctx && (d_sets || n_sets == 0) && n_primers >= 10);
+    if (n_sets == 0) return SWGA_OK;
+    SWGA_NOTE_LAUNCH(); k_synth_sets<<<grid_for(n_sets, 256), 256, 0, as_stream(stream)>>>(seed, start, n_sets, n_primers, d_sets);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -425,9 +466,9 @@ extern "C" int swga_bench_red_global(swga_ctx *ctx, uint32_t *d_table, uint64_t 
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    k_bench_red_global<<<blocks, threads>>>(d_table, (uint32_t)(table_words - 1), 4);   // warm-up
+    SWGA_NOTE_LAUNCH(); k_bench_red_global<<<blocks, threads>>>(d_table, (uint32_t)(table_words - 1), 4);   // warm-up
     CUDA_TRY(cudaEventRecord(e0));
-    k_bench_red_global<<<blocks, threads>>>(d_table, (uint32_t)(table_words - 1), per);
+    SWGA_NOTE_LAUNCH(); k_bench_red_global<<<blocks, threads>>>(d_table, (uint32_t)(table_words - 1), per);
     CUDA_TRY(cudaEventRecord(e1));
     CUDA_TRY(cudaEventSynchronize(e1));
     CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
@@ -447,9 +488,9 @@ extern "C" int swga_bench_atom_shared(swga_ctx *ctx, uint32_t table_words, uint6
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    k_bench_atom_shared<<<blocks, threads, smem>>>(table_words - 1, 4, (uint32_t *)ctx->scratch.p);
+    SWGA_NOTE_LAUNCH(); k_bench_atom_shared<<<blocks, threads, smem>>>(table_words - 1, 4, (uint32_t *)ctx->scratch.p);
     CUDA_TRY(cudaEventRecord(e0));
-    k_bench_atom_shared<<<blocks, threads, smem>>>(table_words - 1, per, (uint32_t *)ctx->scratch.p);
+    SWGA_NOTE_LAUNCH(); k_bench_atom_shared<<<blocks, threads, smem>>>(table_words - 1, per, (uint32_t *)ctx->scratch.p);
     CUDA_TRY(cudaEventRecord(e1));
     CUDA_TRY(cudaEventSynchronize(e1));
     CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));

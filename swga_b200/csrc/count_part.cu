@@ -2,18 +2,27 @@
 // (count.cu), but the updates of the top table T_kmax are taken out of the L2 atomic unit.
 //
 // Round-1 profile (profiles/r01_summary.md): k_count sits at the red.global ceiling (~190 G/s, LTS 87 %)
-// while shared-memory atomics measure ~2600 G/s.  So the kmax-mers are first PARTITIONED by the top
-// `pb` bits of their code into nb = 2^pb buckets (the low 14 bits stored as uint16), and each bucket is
-// then histogrammed in a 2^14-word shared-memory table:
+// while shared-memory atomics measure ~2600 G/s.  So the k-mers are first PARTITIONED by the top bits of
+// their code into buckets, and each bucket is then histogrammed in a shared-memory table.
+//
+// Round 2: the ELEMENT that travels is the (kmax+1)-mer at every EVEN start position.  It holds two
+// consecutive kmax-mers -- its first kmax bases and its last kmax bases -- so one shared-memory slot
+// atomic, one 2-byte staging store and one histogram atomic now serve two table updates (round 1 spent them
+// per k-mer and was bound by exactly these operations: 10.5 + 3.9 shared wavefronts per 32 k-mers).  The
+// element code has 2 (kmax+1) bits: the top `pb` bits select one of nb = 2^pb buckets, the low PT_LB = 15
+// bits are stored as uint16.  The histogram H of a bucket over those 15 bits is turned into table updates
+// when it is flushed, by two linear maps:
+//     first  kmax-mer of an element = code >> 2          : T[(b << 13) | (e >> 2)]          += H[e]
+//     second kmax-mer               = low 2 kmax bits     : T[((b mod 2^(pb-2)) << 15) | e]  += H[e]
 //
 //   (1) k_bucket_hist   counts the prefixes of a strided SAMPLE of the genome (1 warp-tile in `stride`);
 //   (2) k_bucket_layout turns the sample into (a) a global bucket layout -- estimated size + slack per
 //       bucket -- and (b) per-tile slot ranges inside the shared-memory staging area of k_partition;
-//   (3) k_partition     one tile = 16 Ki starts: every element takes its staging slot with ONE shared
-//       atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the whole
-//       16-byte chunks of every bucket's run are then copied to the bucket (one global atomicAdd per
+//   (3) k_partition     one tile = 32 Ki starts = 16 Ki elements: every element takes its staging slot with
+//       ONE shared atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the
+//       whole 16-byte chunks of every bucket's run are then copied to the bucket (one global atomicAdd per
 //       bucket and tile reserves the range), the up to 7 elements left over wait for the next tile;
-//   (4) k_bucket_count  shared-memory histogram of each bucket, added to T_kmax.
+//   (4) k_bucket_count  shared-memory histogram of each bucket, flushed to T_kmax through the two maps.
 //
 // Nothing depends on the sample being right: an element that finds its staging range full goes through
 // a small overflow list, an element that finds its global bucket full is added to T_kmax directly
@@ -24,18 +33,22 @@
 // Reference results reproduced: as count.cu (Bank.cpp:889-902,1042-1070; OAHash.cpp:142-154).
 #include "common.cuh"
 
-#define PT_THREADS 512
-#define PT_TILE (PT_THREADS * 32)                   // 16384 starts per tile, one group of 32 per thread
-#define PT_LB 14                                    // low bits kept per element (uint16), 16384-bin tables
-#define PT_MIN_PB 8                                 // kmax = 11
-#define PT_MAX_PB 10                                // kmax = 12
-#define PT_STAGE 52224u                             // uint16 staging slots per tile (102 KB)
+#define PT_THREADS 1024                             // one CTA per SM
+#define PT_EPG 16                                   // elements per group of 32 starts (the even offsets)
+#define PT_TILE_STARTS (PT_THREADS * 32)            // 32768 starts per tile, one group of 32 per thread
+#define PT_TILE_ELEMS (PT_THREADS * PT_EPG)         // 16384 elements per tile
+#define PT_LB 15                                    // low bits kept per element (uint16), 32768-bin tables
+#define PT_MIN_PB 7                                 // kmax = 10: 2 * 11 - 15
+#define PT_MAX_PB 11                                // kmax = 12: 2 * 13 - 15
+#define PT_STAGE 57344u                             // uint16 staging slots per tile (112 KB)
 #define PT_CH 8                                     // bucket runs are stored in whole 16-byte chunks of 8 elements,
-#define PT_PAD_WORD 0x40004000u                     // padded with values 0x4000 | r (r < PT_PAD_BINS), which land in
-#define PT_PAD_BINS 64                              // dump bins behind k_bucket_count's 2^14-bin table
+#define PT_PAD_WORD 0x80008000u                     // padded with values 0x8000 | r (r < PT_PAD_BINS), which land in
+#define PT_PAD_BINS 64                              // dump bins behind k_bucket_count's 2^15-bin table
 #define PT_OVF_CAP 512u                             // staging-overflow list entries per tile
 #define PT_ADD ((1u << 17) + 2u)                    // one element: guard += 1, byte address += 2
-#define BC_THREADS 512
+#define PT_ITEMS 2                                  // buckets per thread in the single-block layout kernels (nb <= 2048)
+#define HIST_THREADS 512
+#define BC_THREADS 1024
 #define BC_ITEM (1u << 20)                          // elements per work item of k_bucket_count
 
 struct Group {
@@ -120,32 +133,35 @@ __device__ __forceinline__ void slow_group(const uint32_t *__restrict__ packed, 
     }
 }
 
+// both kmax-mers of an element (code = 2 (kmax+1) bits), straight to the top table
+__device__ __forceinline__ void add_element(uint32_t *__restrict__ top, uint32_t code, int kmax)
+{
+    atomicAdd(top + (code >> 2), 1u);
+    atomicAdd(top + (code & ((1u << (2 * kmax)) - 1u)), 1u);
+}
+
 // ---- (1) per-prefix counts of the fast groups of a strided sample ------------------------------------
 // Sampled group i is group (i / 32) * 32 * stride + (i % 32): one warp-tile of 1024 consecutive starts
 // out of every `stride`.
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS)
 k_bucket_hist(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmax,
               int pb, uint64_t n_sampled, uint32_t stride, uint32_t *__restrict__ bucket_cnt)
 {
     extern __shared__ uint32_t h[];
     const uint32_t nb = 1u << pb;
-    for (uint32_t i = threadIdx.x; i < nb; i += PT_THREADS) h[i] = 0;
+    for (uint32_t i = threadIdx.x; i < nb; i += HIST_THREADS) h[i] = 0;
     __syncthreads();
     const int sh = 32 - pb;
-    for (uint64_t i = blockIdx.x * (uint64_t)PT_THREADS + threadIdx.x; i < n_sampled; i += (uint64_t)gridDim.x * PT_THREADS) {
+    for (uint64_t i = blockIdx.x * (uint64_t)HIST_THREADS + threadIdx.x; i < n_sampled; i += (uint64_t)gridDim.x * HIST_THREADS) {
         const uint64_t g = (i >> 5) * 32 * stride + (i & 31);
         const Group G = load_group(packed, brk, g, n_starts, kmax);
-        if (G.fast) {
-            if (uniform_group(G, kmax)) {
-                atomicAdd(&h[G.w0 >> sh], 32u);
-            } else {
+        if (G.fast && !uniform_group(G, kmax)) {               // uniform groups never reach the buckets
 #pragma unroll
-                for (int o = 0; o < 32; ++o) atomicAdd(&h[window(G, o) >> sh], 1u);
-            }
+            for (int o = 0; o < 32; o += 2) atomicAdd(&h[window(G, o) >> sh], 1u);
         }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nb; i += PT_THREADS)
+    for (uint32_t i = threadIdx.x; i < nb; i += HIST_THREADS)
         if (h[i]) atomicAdd(bucket_cnt + i, h[i]);
 }
 
@@ -185,43 +201,76 @@ __host__ __device__ static inline unsigned long long bucket_slack(unsigned long 
     return est / 16 + (unsigned long long)(8.0f * (float)ratio * sqrt_s) + 1024ull;
 }
 
-// single block of 1024 threads; nb <= 1024.  `pad` = expected padding per bucket (runs are stored in
-// chunks of PT_CH elements).
+// exclusive scan over PT_ITEMS consecutive values per thread (bucket b = PT_ITEMS * threadIdx.x + j)
+__device__ __forceinline__ void block_excl_scan_items(const unsigned long long (&v)[PT_ITEMS], unsigned long long (&before)[PT_ITEMS],
+                                                      unsigned long long *s_warp, unsigned long long *total)
+{
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) sum += v[j];
+    unsigned long long run = block_excl_scan_1024(sum, s_warp, total);
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        before[j] = run;
+        run += v[j];
+    }
+}
+
+// single block of 1024 threads; nb <= PT_ITEMS * 1024.  `pad` = expected padding per bucket (runs are stored in
+// chunks of PT_CH elements).  n_groups / n_sampled: groups of 32 starts in the genome / in the sample.
 __global__ void __launch_bounds__(1024)
 k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n_groups, uint64_t n_sampled,
                 uint32_t ratio, uint64_t pad, uint64_t capacity, uint32_t *__restrict__ base,
                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ init)
 {
     __shared__ unsigned long long s_warp[33];
-    const uint32_t b = threadIdx.x;
-    const uint32_t s = b < nb ? sample_cnt[b] : 0u;
+    unsigned long long s[PT_ITEMS], tmp[PT_ITEMS], cap_g[PT_ITEMS], off[PT_ITEMS], cap_t[PT_ITEMS], start[PT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        s[j] = b < nb ? sample_cnt[b] : 0u;
+    }
     unsigned long long S;
-    block_excl_scan_1024(s, s_warp, &S);
+    block_excl_scan_items(s, tmp, s_warp, &S);
     // (a) global layout
-    unsigned long long est = n_sampled ? (unsigned long long)s * n_groups / n_sampled : 0ull;
-    unsigned long long cap_g = 0;
-    if (b < nb) cap_g = (est + bucket_slack(est, sqrtf((float)s + 1.0f), ratio) + pad + 7ull) & ~7ull;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        const unsigned long long est = n_sampled ? s[j] * n_groups / n_sampled : 0ull;
+        cap_g[j] = b < nb ? (est + bucket_slack(est, sqrtf((float)s[j] + 1.0f), ratio) + pad + 7ull) & ~7ull : 0ull;
+    }
     unsigned long long total;
-    unsigned long long off = block_excl_scan_1024(cap_g, s_warp, &total);
-    if (total > capacity) {                                    // cannot happen with the host's bound; stay in range anyway
-        off = (off * capacity / total) & ~7ull;
-        total = capacity & ~7ull;
+    block_excl_scan_items(cap_g, off, s_warp, &total);
+    const bool squeeze = total > capacity;                     // cannot happen with the host's bound; stay in range anyway
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        unsigned long long o = off[j];
+        if (squeeze) o = (o * capacity / total) & ~7ull;
+        if (b < nb) {
+            base[b] = (uint32_t)o;
+            cursor[b] = (uint32_t)o;
+        }
     }
-    if (b < nb) {
-        base[b] = (uint32_t)off;
-        cursor[b] = (uint32_t)off;
-    }
-    if (b == 0) base[nb] = (uint32_t)total;
+    if (threadIdx.x == 0) base[nb] = (uint32_t)(squeeze ? capacity & ~7ull : total);
     // (b) staging slots per tile: 5/4 of the expected share of the tile + beta, a multiple of 8
-    const uint32_t beta = (PT_STAGE - PT_TILE * 5 / 4) / nb - 8;
-    unsigned long long cap_t = 0;
-    if (b < nb) {
-        const unsigned long long share = S ? (unsigned long long)s * (PT_TILE * 5 / 4) / S : 0ull;
-        cap_t = (min((unsigned long long)PT_TILE, share + beta) + 7ull) & ~7ull;
+    const uint32_t beta = (PT_STAGE - PT_TILE_ELEMS * 5 / 4) / nb - 8;
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        cap_t[j] = 0;
+        if (b < nb) {
+            const unsigned long long share = S ? s[j] * (PT_TILE_ELEMS * 5 / 4) / S : 0ull;
+            cap_t[j] = (min((unsigned long long)PT_TILE_ELEMS, share + beta) + 7ull) & ~7ull;
+        }
     }
     unsigned long long tot_t;
-    const unsigned long long start = block_excl_scan_1024(cap_t, s_warp, &tot_t);
-    if (b < nb) init[b] = ((0x4000u - (uint32_t)cap_t) << 17) | (uint32_t)(start * 2);
+    block_excl_scan_items(cap_t, start, s_warp, &tot_t);
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        if (b < nb) init[b] = ((0x4000u - (uint32_t)cap_t[j]) << 17) | (uint32_t)(start[j] * 2);
+    }
 }
 
 // ---- (3) scatter the low bits into prefix buckets --------------------------------------------------
@@ -242,13 +291,14 @@ __device__ __forceinline__ uint4 pad_partial_chunk(uint4 v, uint32_t nv, uint32_
 }
 
 template <int KMAX>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+__global__ void __launch_bounds__(PT_THREADS, 1)
 k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
             uint32_t *__restrict__ tables, TableOffs offs, const uint32_t *__restrict__ base,
             const uint32_t *__restrict__ init_g, uint32_t *__restrict__ cursor, uint16_t *__restrict__ data,
             uint32_t n_tiles, unsigned long long *__restrict__ stats)
 {
-    constexpr int PB = 2 * KMAX - PT_LB, SH = 32 - 2 * KMAX;
+    constexpr int KE = KMAX + 1;                               // bases per element
+    constexpr int PB = 2 * KE - PT_LB, SH = 32 - 2 * KMAX, SHE = 32 - 2 * KE;
     constexpr uint32_t NB = 1u << PB, LMASK = (1u << PT_LB) - 1u;
     constexpr int WARPS = PT_THREADS / 32, UNITS = NB / 32;      // a unit = 32 buckets, one per lane
     constexpr int ROUNDS = (UNITS + WARPS - 1) / WARPS;        // units per warp
@@ -264,7 +314,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     if (tid < 4) s_stats[tid] = 0;
 
     // Padding (only the last chunk a CTA writes into a bucket, and the chunks of the overflow list, carry any):
-    // values 0x4000 | r, r < 64, which land in k_bucket_count's dump bins, spread so that they do not pile up
+    // values 0x8000 | r, r < 64, which land in k_bucket_count's dump bins, spread so that they do not pile up
     // on one shared-memory word.
     uint4 padv;
     {
@@ -284,6 +334,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
 
     uint32_t par = 0;
     RawGroup R = prefetch_group(packed, brk, (uint64_t)blockIdx.x * PT_THREADS + tid, n_starts);
+    static_assert(NB <= PT_ITEMS * 1024 && (NB % 32) == 0, "bucket count");
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t g = (uint64_t)tile * PT_THREADS + tid;
         const Group G = finish_group(R, g, n_starts, KMAX);
@@ -295,24 +346,25 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 atomicAdd(top + (G.w0 >> SH), 32u);
                 atomicAdd(&s_stats[2], 1u);
             } else {
-                uint32_t full = 0;                             // bit 31-o: element o found its range full
+                uint32_t full = 0;                             // bit 15-e: element e (offset 2e) found its range full
 #pragma unroll
-                for (int o = 0; o < 32; ++o) {
+                for (int o = 0; o < 32; o += 2) {
                     const uint32_t W = window(G, o);
                     const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
                     const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
                     // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on
                     // a 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
                     if ((int32_t)old >= 0)
-                        *reinterpret_cast<uint16_t *>(stg + ((old & 0x1FFFFu) ^ ((boff >> 1) & 0xEu))) = (uint16_t)((W >> SH) & LMASK);
+                        *reinterpret_cast<uint16_t *>(stg + ((old & 0x1FFFFu) ^ ((boff >> 1) & 0xEu))) = (uint16_t)((W >> SHE) & LMASK);
                     full = __funnelshift_l(old, full, 1);
                 }
                 while (full) {                                 // rare: the tile's composition is off the sample's
-                    const int o = __clz(full);
-                    full &= ~(0x80000000u >> o);
+                    const int e = __clz(full) - 16;
+                    full &= ~(0x8000u >> e);
+                    const uint32_t code = window(G, 2 * e) >> SHE;
                     const uint32_t slot = atomicAdd(&s_novf[par], 1u);
-                    if (slot < PT_OVF_CAP) ovf[slot] = window(G, o) >> SH;
-                    else atomicAdd(top + (window(G, o) >> SH), 1u);   // list full too: straight to the table
+                    if (slot < PT_OVF_CAP) ovf[slot] = code;
+                    else add_element(top, code, KMAX);         // list full too: straight to the table
                 }
             }
         } else {
@@ -359,7 +411,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                     v.x = (v.x & 0xFFFF0000u) | (code & LMASK);
                     *reinterpret_cast<uint4 *>(data + at) = v;
                 } else {
-                    atomicAdd(top + code, 1u);
+                    add_element(top, code, KMAX);
                     atomicAdd(&s_stats[1], 1u);
                 }
             }
@@ -400,7 +452,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                             for (int q = 0; q < 8; ++q) {
                                 const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
                                 if (e <= LMASK) {
-                                    atomicAdd(top + (((b0 + k) << PT_LB) | e), 1u);
+                                    add_element(top, ((b0 + k) << PT_LB) | e, KMAX);
                                     atomicAdd(&s_stats[1], 1u);
                                 }
                             }
@@ -430,18 +482,26 @@ __global__ void __launch_bounds__(1024)
 k_item_prefix(const uint32_t *__restrict__ bucket_base, const uint32_t *__restrict__ cursor, uint32_t nb,
               uint32_t *__restrict__ item_prefix)
 {
-    // single block of 1024 threads; nb <= 1024
+    // single block of 1024 threads; nb <= PT_ITEMS * 1024
     __shared__ unsigned long long s_warp[33];
-    const uint32_t b = threadIdx.x;
-    unsigned long long items = 0;
-    if (b < nb) {
-        const uint32_t sz = min(cursor[b], bucket_base[b + 1]) - bucket_base[b];
-        items = (sz + BC_ITEM - 1) / BC_ITEM;
+    unsigned long long items[PT_ITEMS], before[PT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        items[j] = 0;
+        if (b < nb) {
+            const uint32_t sz = min(cursor[b], bucket_base[b + 1]) - bucket_base[b];
+            items[j] = (sz + BC_ITEM - 1) / BC_ITEM;
+        }
     }
     unsigned long long total;
-    const unsigned long long before = block_excl_scan_1024(items, s_warp, &total);
-    if (b < nb) item_prefix[b] = (uint32_t)before;
-    if (b == 0) item_prefix[nb] = (uint32_t)total;
+    block_excl_scan_items(items, before, s_warp, &total);
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; ++j) {
+        const uint32_t b = PT_ITEMS * threadIdx.x + j;
+        if (b < nb) item_prefix[b] = (uint32_t)before[j];
+    }
+    if (threadIdx.x == 0) item_prefix[nb] = (uint32_t)total;
 }
 
 // ---- (4) shared-memory histogram of each bucket, added to the top table ------------------------------
@@ -459,7 +519,7 @@ __device__ __forceinline__ void count8(uint32_t *tab, const uint4 x)
 
 __global__ void __launch_bounds__(BC_THREADS)
 k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restrict__ bucket_base,
-               const uint32_t *__restrict__ cursor, const uint32_t *__restrict__ item_prefix, uint32_t nb, int lb,
+               const uint32_t *__restrict__ cursor, const uint32_t *__restrict__ item_prefix, uint32_t nb, int lb, int pb,
                uint32_t *__restrict__ top, uint32_t *__restrict__ work_counter)
 {
     extern __shared__ uint32_t tab[];
@@ -498,10 +558,18 @@ k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restr
         for (; i < nv; i += BC_THREADS) count8(tab, __ldcs(v + i));
         for (uint32_t j = aend + threadIdx.x; j < end; j += BC_THREADS) count1(tab, bucket_data[j]);
         __syncthreads();
-        uint32_t *dst = top + ((uint64_t)b << lb);
+        // flush: H[e] counts elements of code (b << lb | e); each is two kmax-mers (see the head of this file)
+        uint32_t *dst2 = top + ((uint64_t)(b & ((1u << (pb - 2)) - 1u)) << lb);    // second k-mer: low 2 kmax bits of the code
         for (uint32_t j = threadIdx.x; j < bins; j += BC_THREADS) {
             const uint32_t c = tab[j];
-            if (c) atomicAdd(dst + j, c);
+            if (c) atomicAdd(dst2 + j, c);
+        }
+        uint32_t *dst1 = top + ((uint64_t)b << (lb - 2));                          // first k-mer: code >> 2
+        const uint4 *tab4 = reinterpret_cast<const uint4 *>(tab);
+        for (uint32_t t = threadIdx.x; t < (bins >> 2); t += BC_THREADS) {
+            const uint4 q = tab4[t];
+            const uint32_t c = q.x + q.y + q.z + q.w;
+            if (c) atomicAdd(dst1 + t, c);
         }
         __syncthreads();
     }
@@ -509,7 +577,7 @@ k_bucket_count(const uint16_t *__restrict__ bucket_data, const uint32_t *__restr
 
 int swga_count_partition_supported(uint64_t n_starts, int kmax, int *ok)
 {
-    const int pb = 2 * kmax - PT_LB;
+    const int pb = 2 * (kmax + 1) - PT_LB;
     *ok = !(pb < PT_MIN_PB || pb > PT_MAX_PB || n_starts < (1u << 22) || n_starts > 0xE0000000ull);
     return SWGA_OK;
 }
@@ -520,7 +588,7 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
                                       int kmin, int kmax, uint32_t *d_tables, cudaStream_t stream, int *done)
 {
     *done = 0;
-    const int pb = 2 * kmax - PT_LB;
+    const int pb = 2 * (kmax + 1) - PT_LB;
     int ok = 0;
     swga_count_partition_supported(n_starts, kmax, &ok);
     if (!ok) return SWGA_OK;
@@ -532,10 +600,10 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     const uint64_t n_sampled = (n_groups / (32ull * stride)) * 32 + std::min<uint64_t>(32, n_groups % (32ull * stride));
     const uint32_t ratio = (uint32_t)((n_groups + n_sampled - 1) / n_sampled);
     // upper bound of the layout (sum of estimate + slack over the buckets; Cauchy-Schwarz on the sqrt terms)
-    const double s_tot = (double)n_sampled * 32.0;
-    const uint32_t n_tiles = (uint32_t)((n_starts + PT_TILE - 1) / PT_TILE);
+    const double s_tot = (double)n_sampled * PT_EPG;
+    const uint32_t n_tiles = (uint32_t)((n_starts + PT_TILE_STARTS - 1) / PT_TILE_STARTS);
     const uint64_t pad = 2ull * ctx->sm_count * PT_CH;         // padding per bucket: one partial chunk per CTA, with its last tile
-    const uint64_t capacity = (uint64_t)((double)n_groups * 32.0 * (17.0 / 16.0) + 8.0 * ratio * sqrt((double)nb * (s_tot + nb)) +
+    const uint64_t capacity = (uint64_t)((double)n_groups * PT_EPG * (17.0 / 16.0) + 8.0 * ratio * sqrt((double)nb * (s_tot + nb)) +
                                          (1033.0 + (double)pad) * nb + 64.0 * ratio + 4096.0);
     if (capacity >= 0xFFFFFFF0ull) return SWGA_OK;            // offsets are 32-bit
     // workspace: bucket data (2 B per slot) + sample[nb] + base[nb+1] + cursor[nb] + init[nb] + item_prefix[nb+1] + work
@@ -557,27 +625,29 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
             if (!ctx->ev_stage[i]) CUDA_TRY(cudaEventCreate(&ctx->ev_stage[i]));
         CUDA_TRY(cudaEventRecord(ctx->ev_stage[0], stream));
     }
-    const int grid_h = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (n_sampled + PT_THREADS - 1) / PT_THREADS);
-    k_bucket_hist<<<grid_h, PT_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
-    k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
+    const int grid_h = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (n_sampled + HIST_THREADS - 1) / HIST_THREADS);
+    SWGA_NOTE_LAUNCH(); k_bucket_hist<<<grid_h, HIST_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
+    SWGA_NOTE_LAUNCH(); k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
     if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[1], stream));
     const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_STAGE * 2;
-    const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 2);
-    if (kmax == 12) {
-        CUDA_TRY(cudaFuncSetAttribute(k_partition<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-        k_partition<12><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base, init,
-                                                                cursor, data, n_tiles, stats);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_partition<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-        k_partition<11><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base, init,
-                                                                cursor, data, n_tiles, stats);
-    }
+    const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
+#define LAUNCH_PARTITION(K)                                                                                              \
+    do {                                                                                                                 \
+        CUDA_TRY(cudaFuncSetAttribute(k_partition<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));        \
+        SWGA_NOTE_LAUNCH();                                                                                              \
+        k_partition<K><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base,    \
+                                                               init, cursor, data, n_tiles, stats);                      \
+    } while (0)
+    if (kmax == 12) LAUNCH_PARTITION(12);
+    else if (kmax == 11) LAUNCH_PARTITION(11);
+    else LAUNCH_PARTITION(10);
+#undef LAUNCH_PARTITION
     if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[2], stream));
-    k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);
+    SWGA_NOTE_LAUNCH(); k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);
     const size_t smem_c = ((size_t)4 << PT_LB) + 4 * PT_PAD_BINS;
     CUDA_TRY(cudaFuncSetAttribute(k_bucket_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    k_bucket_count<<<ctx->sm_count * 3, BC_THREADS, smem_c, stream>>>(data, base, cursor, item_prefix, nb, PT_LB,
-                                                                     d_tables + offs.off[kmax], work);
+    SWGA_NOTE_LAUNCH(); k_bucket_count<<<ctx->sm_count, BC_THREADS, smem_c, stream>>>(data, base, cursor, item_prefix, nb, PT_LB, pb,
+                                                                 d_tables + offs.off[kmax], work);
     CUDA_TRY(cudaGetLastError());
     if (timing) {
         CUDA_TRY(cudaEventRecord(ctx->ev_stage[3], stream));

@@ -55,7 +55,7 @@ extern "C" int swga_filter_primers(swga_ctx *ctx, const uint32_t *d_canon_fg, co
     const uint64_t total = swga_tables_words(kmin, kmax);
     CUDA_TRY(cudaMemsetAsync(d_n_rows, 0, 4, as_stream(stream)));
     const uint32_t max_bg = max_bg_bind < 0 ? 0xffffffffu : (max_bg_bind > 0xffffffffll ? 0xffffffffu : (uint32_t)max_bg_bind);
-    k_filter_primers<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+    SWGA_NOTE_LAUNCH(); k_filter_primers<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         d_canon_fg, d_canon_bg, d_canon_ex, kmin, kmax, swga_make_offs(kmin, kmax), total, min_fg_bind, max_bg, max_dimer_bp,
         exclude_threshold ? exclude_threshold : 1u, reinterpret_cast<uint4 *>(d_rows), d_n_rows, row_capacity);
     CUDA_TRY(cudaGetLastError());

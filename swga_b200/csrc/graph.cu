@@ -84,7 +84,7 @@ extern "C" int swga_build_edges(swga_ctx *ctx, const uint8_t *d_seqs, uint32_t n
     }
     if (n == 0) return SWGA_OK;
     const dim3 grid((n + GE_THREADS - 1) / GE_THREADS, n);
-    k_build_edges<<<grid, GE_THREADS, 0, as_stream(stream)>>>(d_seqs, n, stride, d_len, max_binding, d_adj, words_per_row);
+    SWGA_NOTE_LAUNCH(); k_build_edges<<<grid, GE_THREADS, 0, as_stream(stream)>>>(d_seqs, n, stride, d_len, max_binding, d_adj, words_per_row);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }

@@ -113,9 +113,9 @@ int swga_exclusive_scan(swga_ctx *ctx, const uint32_t *d_in, uint64_t n, uint32_
     const uint32_t n_part = (uint32_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
     TRY(swga_ensure(ctx, ctx->scratch, (size_t)n_part * 4 + 256));
     uint32_t *partial = (uint32_t *)ctx->scratch.p;
-    k_scan_reduce<<<n_part, SCAN_THREADS, 0, stream>>>(d_in, n, partial);
-    k_scan_partials<<<1, 1024, 0, stream>>>(partial, n_part, d_total);
-    k_scan_apply<<<n_part, SCAN_THREADS, 0, stream>>>(d_in, n, partial, d_out);
+    SWGA_NOTE_LAUNCH(); k_scan_reduce<<<n_part, SCAN_THREADS, 0, stream>>>(d_in, n, partial);
+    SWGA_NOTE_LAUNCH(); k_scan_partials<<<1, 1024, 0, stream>>>(partial, n_part, d_total);
+    SWGA_NOTE_LAUNCH(); k_scan_apply<<<n_part, SCAN_THREADS, 0, stream>>>(d_in, n, partial, d_out);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -237,9 +237,9 @@ int swga_radix_sort_pairs(swga_ctx *ctx, uint32_t *keys_a, uint32_t *vals_a, uin
     for (int shift = 0; shift < bits; shift += 8) {
         uint32_t *ki = in_a ? keys_a : keys_b, *vi = in_a ? vals_a : vals_b;
         uint32_t *ko = in_a ? keys_b : keys_a, *vo = in_a ? vals_b : vals_a;
-        k_rs_upsweep<<<n_tiles, RS_THREADS, 0, stream>>>(ki, n, shift, th, n_tiles);
+        SWGA_NOTE_LAUNCH(); k_rs_upsweep<<<n_tiles, RS_THREADS, 0, stream>>>(ki, n, shift, th, n_tiles);
         TRY(swga_exclusive_scan(ctx, th, (uint64_t)256 * n_tiles, th, nullptr, stream));
-        k_rs_downsweep<<<n_tiles, RS_THREADS, 0, stream>>>(ki, (first && vals_are_index) ? nullptr : vi, ko, vo, n,
+        SWGA_NOTE_LAUNCH(); k_rs_downsweep<<<n_tiles, RS_THREADS, 0, stream>>>(ki, (first && vals_are_index) ? nullptr : vi, ko, vo, n,
                                                            shift, th, n_tiles);
         CUDA_TRY(cudaGetLastError());
         in_a = !in_a;
@@ -270,7 +270,7 @@ extern "C" int swga_build_index(swga_ctx *ctx, const uint32_t *d_packed, const u
     TRY(swga_ensure(ctx, ctx->sort_vals[1], n * 4));
     uint32_t *ka = (uint32_t *)ctx->sort_keys[0].p, *kb = (uint32_t *)ctx->sort_keys[1].p;
     uint32_t *va = (uint32_t *)ctx->sort_vals[0].p, *vb = (uint32_t *)ctx->sort_vals[1].p;
-    k_index_keys<<<grid_for((n + 31) / 32, 256), 256, 0, stream>>>(d_packed, d_brk, n, k, ka, d_offsets);
+    SWGA_NOTE_LAUNCH(); k_index_keys<<<grid_for((n + 31) / 32, 256), 256, 0, stream>>>(d_packed, d_brk, n, k, ka, d_offsets);
     CUDA_TRY(cudaGetLastError());
     // offsets = exclusive scan of the histogram (nbins entries) with the grand total in slot nbins
     TRY(swga_exclusive_scan(ctx, d_offsets, nbins, d_offsets, d_offsets + nbins, stream));
@@ -306,7 +306,7 @@ extern "C" int swga_locate_counts(swga_ctx *ctx, int k, const uint32_t *d_offset
 {
     ARG_CHECK(ctx && d_offsets && (d_codes || q == 0) && (d_counts || q == 0) && k >= 2 && k <= SWGA_KMAX_LIMIT);
     if (q == 0) return SWGA_OK;
-    k_locate_counts<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(d_offsets, d_codes, q, d_counts);
+    SWGA_NOTE_LAUNCH(); k_locate_counts<<<grid_for(q, 256), 256, 0, as_stream(stream)>>>(d_offsets, d_codes, q, d_counts);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -318,7 +318,7 @@ extern "C" int swga_locate_gather(swga_ctx *ctx, int k, const uint32_t *d_offset
     ARG_CHECK(ctx && d_offsets && (d_codes || q == 0) && k >= 2 && k <= SWGA_KMAX_LIMIT);
     if (q == 0) return SWGA_OK;
     ARG_CHECK(d_out_off && d_out);
-    k_locate_gather<<<q, 256, 0, as_stream(stream)>>>(d_offsets, d_positions, d_codes, d_out_off, d_out);
+    SWGA_NOTE_LAUNCH(); k_locate_gather<<<q, 256, 0, as_stream(stream)>>>(d_offsets, d_positions, d_codes, d_out_off, d_out);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -356,7 +356,7 @@ extern "C" int swga_union_strands(swga_ctx *ctx, const uint32_t *d_hits, const u
     ARG_CHECK(ctx);
     if (n_primers == 0) return SWGA_OK;
     ARG_CHECK(d_hits && d_hit_off && d_is_pal && d_out_off && d_out);
-    k_union2<<<n_primers, 256, 0, as_stream(stream)>>>(d_hits, d_hit_off, d_is_pal, d_out_off, d_out);
+    SWGA_NOTE_LAUNCH(); k_union2<<<n_primers, 256, 0, as_stream(stream)>>>(d_hits, d_hit_off, d_is_pal, d_out_off, d_out);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -381,7 +381,7 @@ extern "C" int swga_tile_offsets(swga_ctx *ctx, const uint32_t *d_sites, const u
 {
     ARG_CHECK(ctx && d_site_off && d_toff && tile_shift >= 5 && tile_shift < 32);
     if (n_lists == 0) return SWGA_OK;
-    k_tile_offsets<<<grid_for((uint64_t)n_lists * (n_tiles + 1), 256), 256, 0, as_stream(stream)>>>(
+    SWGA_NOTE_LAUNCH(); k_tile_offsets<<<grid_for((uint64_t)n_lists * (n_tiles + 1), 256), 256, 0, as_stream(stream)>>>(
         d_sites, d_site_off, n_lists, tile_shift, n_tiles, d_toff);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;

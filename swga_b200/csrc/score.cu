@@ -1069,14 +1069,14 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
     uint32_t *n_ids = a.work + 2, *ids = (uint32_t *)((uint8_t *)ctx->score_tmp.p + 256);
     CUDA_TRY(cudaMemsetAsync(a.work, 0, 16, as_stream(stream)));
     if (a.sort_cap) {
-        k_score_classify<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(a, ids, n_ids);
+        SWGA_NOTE_LAUNCH(); k_score_classify<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(a, ids, n_ids);
         CUDA_TRY(cudaGetLastError());
         a.ids = ids; a.n_ids = n_ids;
         const size_t smem_s = 8ull * MS_PHYS(a.sort_cap + SS_RUN_PAD);
         CUDA_TRY(cudaFuncSetAttribute(k_score_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem_s + 1024)));
         const uint32_t grid_s = std::min<uint32_t>(S, (uint32_t)ctx->sm_count * per_sm);
-        k_score_sort<<<grid_s, SS_THREADS, smem_s, as_stream(stream)>>>(a);
+        SWGA_NOTE_LAUNCH(); k_score_sort<<<grid_s, SS_THREADS, smem_s, as_stream(stream)>>>(a);
         CUDA_TRY(cudaGetLastError());
     }
     // the rest: one warp per fine tile (k_score_dense)
@@ -1087,11 +1087,11 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         a.ids = ids + S;
         a.n_ids = n_ids + 1;
     } else {                                                   // no sparse kernel: every set is "dense"
-        k_score_all_ids<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(ids + S, n_ids + 1, S);
+        SWGA_NOTE_LAUNCH(); k_score_all_ids<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(ids + S, n_ids + 1, S);
         a.ids = ids + S;
         a.n_ids = n_ids + 1;
     }
-    k_score_dense<<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
+    SWGA_NOTE_LAUNCH(); k_score_dense<<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
@@ -1131,7 +1131,7 @@ extern "C" int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const
     a.gap_count = (uint32_t *)(tmp + 16);
     const size_t smem = 4ull * (SC_L0_PHYS + SC_L1_WORDS);
     CUDA_TRY(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_score<<<1, SC_THREADS, smem, stream>>>(a);
+    SWGA_NOTE_LAUNCH(); k_score<<<1, SC_THREADS, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     uint32_t ng = 0;
     CUDA_TRY(cudaMemcpyAsync(&ng, tmp + 16, 4, cudaMemcpyDeviceToHost, stream));
@@ -1144,7 +1144,7 @@ extern "C" int swga_gini_unbounded(swga_ctx *ctx, const uint32_t *d_sites, const
     TRY(swga_radix_sort_pairs(ctx, (uint32_t *)ctx->sort_keys[0].p, (uint32_t *)ctx->sort_vals[0].p,
                               (uint32_t *)ctx->sort_keys[1].p, (uint32_t *)ctx->sort_vals[1].p, ng, 32, true, &in_a,
                               stream));
-    k_gini_sorted<<<1, SC_THREADS, 0, stream>>>((const uint32_t *)ctx->sort_keys[in_a ? 0 : 1].p, ng,
+    SWGA_NOTE_LAUNCH(); k_gini_sorted<<<1, SC_THREADS, 0, stream>>>((const uint32_t *)ctx->sort_keys[in_a ? 0 : 1].p, ng,
                                                 (double *)(tmp + 8));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_gini, tmp + 8, 8, cudaMemcpyDeviceToHost, stream));

@@ -58,3 +58,39 @@ def allreduce_tables(d_fwd):
     if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
         td.all_reduce(d_fwd, op=td.ReduceOp.SUM)
     return d_fwd
+
+
+class TableMerge(object):
+    """The cross-GPU merge of the additive table blocks, as two halves so that other work (the replicated
+    foreground count) can be enqueued in between:
+
+        block()                     the device block this rank accumulates its background shard into
+        start(d_fwd)                begin merging (asynchronous with respect to the caller's stream)
+        finish(d_fwd, d_canon)      wait, then leave the FINALIZED forward tables in d_fwd and the canonical
+                                    tables in d_canon on every rank
+
+    This implementation: one NCCL all_reduce(SUM) of the block over NVLink, then finalize + fold on every rank.
+    `events` (optional pair of CUDA events) brackets the time the caller's stream spends waiting for the merge."""
+
+    name = "nccl all_reduce(sum, 89.5 MB) + finalize + fold on every rank"
+
+    def __init__(self, words, kmin, kmax, device):
+        self.words, self.kmin, self.kmax, self.device = words, kmin, kmax, device
+        self.work = None
+
+    def block(self):
+        import torch
+        return torch.empty(self.words, dtype=torch.int32, device=self.device)
+
+    def start(self, d_fwd, events=None):
+        import torch.distributed as td
+        self.work = td.all_reduce(d_fwd, op=td.ReduceOp.SUM, async_op=True)
+
+    def finish(self, d_fwd, d_canon, events=None):
+        if events is not None:
+            events[0].record()
+        self.work.wait()
+        self.work = None
+        if events is not None:
+            events[1].record()
+        finalize_tables(d_fwd, self.kmin, self.kmax, d_canon)
