@@ -52,6 +52,8 @@ def parse_args():
                     help="reference arm: shrink the sample so that all timed steps fit this many seconds")
     ap.add_argument("--score-sets", type=float, default=1e7, help="candidate sets of the 'typical' scoring workload")
     ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
+                    help="cross-GPU merge: the fused peer-memory kernel (default) or NCCL all_reduce + finalize on every rank")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -308,7 +310,7 @@ def run_b200_arm(args):
     lib, ctx = _lib.load(), _lib.context(local)
     P = _lib.ptr
     words = int(lib.swga_tables_words(KMIN, KMAX))
-    merge = dist.TableMerge(words, KMIN, KMAX, dev) if world > 1 else None
+    merge = dist.table_merge(words, KMIN, KMAX, dev, prefer=args.merge) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()

@@ -138,6 +138,17 @@ int swga_count_stage_ms(swga_ctx *ctx, float *h_ms);
 int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd,
                         uint32_t *d_canon, void *stream);
 
+/* The cross-GPU merge of the ranks' additive blocks fused with swga_count_finalize (csrc/merge.cu): h_blocks holds
+ * `world` (2, 4 or 8) device pointers -- this rank's peer mappings of every rank's block, in rank order, e.g. the
+ * buffer_ptrs of a torch symmetric-memory allocation.  Rank r sums, finalizes and writes back, into ALL blocks,
+ * the slice [r, r + 1) / world of every table; when all ranks have run it (the caller puts a barrier across the
+ * ranks before and after), every block holds the finalized forward tables of the whole genome.  Needs
+ * kmax - kmin <= 7 (swga_merge_supported).  With all pointers on one device and the ranks run one after another
+ * it is also a plain multi-block sum + finalize (tests). */
+int swga_merge_supported(int kmin, int kmax, int world, int *ok);
+int swga_merge_finalize(swga_ctx *ctx, const uint64_t *h_blocks, int world, int rank, int kmin, int kmax,
+                        void *stream);
+
 /* Whole counting pass on a device-resident genome: pack + mark + accumulate + finalize + fold,
  * using context-owned workspaces.  d_canon (and d_fwd if non-NULL) receive swga_tables_words()
  * words.  `finalize` = 0 leaves d_fwd in the additive form and skips the fold (multi-GPU: allreduce

@@ -1,0 +1,126 @@
+// merge.cu -- the cross-GPU merge of the additive count-table blocks, fused with the finalize pass.
+//
+// Every rank has accumulated its shard of the genome into its own block (additive "top-k + tails" form,
+// include/swga_b200.h).  The reference of this step is a sum over ranks followed by the prefix marginalisation
+// T_k[x] += sum_b T_{k+1}[4x + b] (swga_count_finalize).  Round 1 did it as an NCCL all_reduce of the 89.5 MB
+// block plus finalize on every rank: every rank summed and marginalised EVERYTHING.
+//
+// Here the code space is split by its leading bits: rank r owns, at every level k, the codes whose position
+// in the table is in [r, r + 1) / world -- and the children of an owned code are owned too.  One kernel per
+// rank, over the peer mappings of all blocks (NVLink / NVSwitch loads and stores, no staging copy, no NCCL):
+//
+//     for its span of 4^d codes of T_kmax a CTA loads the 16-byte words of ALL ranks' blocks, sums them,
+//     stores the sum into ALL ranks' blocks (in place: only the owner ever touches an owned word), and keeps
+//     the four-way sums in shared memory; these are the marginal part of the level below, to which it adds the
+//     ranks' tail counts of that level (same load / sum / store), and so on down to kmin.
+//
+// Afterwards every block holds the FINALIZED forward tables of the whole genome: reduce-scatter, finalize of
+// the owned slice and all-gather in one pass; each rank sums and marginalises 1 / world of the tables.
+// The caller brackets the kernel with two device-side barriers across the ranks (swga_b200/dist.py).
+#include "common.cuh"
+
+#define MG_THREADS 256
+#define MG_MAX_WORLD 8
+#define MG_MAX_DEPTH 7                              // levels below kmax finished inside one CTA: span = 4^7 codes of T_kmax
+
+struct PeerBlocks {
+    uint32_t *p[MG_MAX_WORLD];
+};
+
+__device__ __forceinline__ uint4 ld_peer(const uint32_t *a)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a));
+    return v;
+}
+__device__ __forceinline__ void st_peer(uint32_t *a, const uint4 v)
+{
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One CTA: `span` consecutive codes of level kmax starting at code c0 (span = 4^depth), then the span / 4 codes of
+// level kmax - 1 starting at c0 / 4, ... down to level kmax - depth.
+template <int WORLD>
+__global__ void __launch_bounds__(MG_THREADS)
+k_merge_finalize(PeerBlocks blocks, TableOffs offs, int kmax, int depth, uint64_t slice_start, uint32_t span)
+{
+    // marg[i] = sum of the four children of code i of the level being processed (the marginal part of its value)
+    __shared__ __align__(16) uint32_t bufA[4096], bufB[1024];
+    uint32_t *marg = bufA, *next = bufB;
+    uint64_t c0 = slice_start + (uint64_t)blockIdx.x * span;
+    uint32_t n = span;                                         // codes of this level in the CTA's span
+    for (int lv = 0; lv <= depth; ++lv) {
+        const int k = kmax - lv;
+        const uint64_t off = offs.off[k] + c0;
+        uint32_t *out = lv == 0 ? marg : next;                 // where this level's four-way sums go
+        if (n >= 4) {
+            for (uint32_t i = threadIdx.x; i < n / 4; i += MG_THREADS) {
+                uint4 v[WORLD];
+#pragma unroll
+                for (int p = 0; p < WORLD; ++p) v[p] = ld_peer(blocks.p[p] + off + 4ull * i);
+                uint4 s = v[0];
+#pragma unroll
+                for (int p = 1; p < WORLD; ++p) {
+                    s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w;
+                }
+                if (lv > 0) {
+                    const uint4 m = reinterpret_cast<const uint4 *>(marg)[i];
+                    s.x += m.x; s.y += m.y; s.z += m.z; s.w += m.w;
+                }
+#pragma unroll
+                for (int p = 0; p < WORLD; ++p) st_peer(blocks.p[p] + off + 4ull * i, s);
+                out[i] = s.x + s.y + s.z + s.w;
+            }
+        } else if (threadIdx.x == 0) {                         // n == 1: the last level of the span
+            uint32_t s = lv > 0 ? marg[0] : 0u;
+#pragma unroll
+            for (int p = 0; p < WORLD; ++p) s += *reinterpret_cast<volatile const uint32_t *>(blocks.p[p] + off);
+#pragma unroll
+            for (int p = 0; p < WORLD; ++p) *reinterpret_cast<volatile uint32_t *>(blocks.p[p] + off) = s;
+        }
+        __syncthreads();
+        if (lv > 0) {                                          // `next` becomes the marginals of the level below
+            uint32_t *t = marg;
+            marg = next;
+            next = t;
+        }
+        c0 >>= 2;
+        n >>= 2;
+    }
+}
+
+extern "C" int swga_merge_supported(int kmin, int kmax, int world, int *ok)
+{
+    ARG_CHECK(ok);
+    const int depth = kmax - kmin;
+    // a rank's slice of T_kmax must be whole spans of 4^depth codes
+    *ok = kmin >= 2 && kmax <= SWGA_KMAX_LIMIT && depth >= 0 && depth <= MG_MAX_DEPTH && (world == 2 || world == 4 || world == 8) &&
+          ((1ull << (2 * kmax)) / (unsigned)world) % (1ull << (2 * depth)) == 0;
+    return SWGA_OK;
+}
+
+// h_blocks: `world` device pointers (this rank's view: peer mappings) of the ranks' table blocks, in rank order.
+extern "C" int swga_merge_finalize(swga_ctx *ctx, const uint64_t *h_blocks, int world, int rank, int kmin, int kmax, void *stream)
+{
+    ARG_CHECK(ctx && h_blocks && rank >= 0 && rank < world);
+    int ok = 0;
+    TRY(swga_merge_supported(kmin, kmax, world, &ok));
+    if (!ok) {
+        swga_set_error("swga_merge_finalize: unsupported shape kmin=%d kmax=%d world=%d", kmin, kmax, world);
+        return SWGA_E_ARG;
+    }
+    PeerBlocks pb;
+    for (int i = 0; i < MG_MAX_WORLD; ++i) pb.p[i] = reinterpret_cast<uint32_t *>(i < world ? h_blocks[i] : 0);
+    const TableOffs offs = swga_make_offs(kmin, kmax);
+    const int depth = kmax - kmin;
+    const uint64_t slice = (1ull << (2 * kmax)) / (unsigned)world;
+    const uint32_t span = 1u << (2 * depth);
+    const unsigned grid = (unsigned)(slice / span);
+    cudaStream_t st = as_stream(stream);
+    SWGA_NOTE_LAUNCH();
+    if (world == 2) k_merge_finalize<2><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
+    else if (world == 4) k_merge_finalize<4><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
+    else k_merge_finalize<8><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
+    CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}

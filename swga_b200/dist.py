@@ -94,3 +94,76 @@ class TableMerge(object):
         if events is not None:
             events[1].record()
         finalize_tables(d_fwd, self.kmin, self.kmax, d_canon)
+
+
+class PeerTableMerge(TableMerge):
+    """The merge as ONE kernel per rank over NVLink peer mappings (csrc/merge.cu, swga_merge_finalize): reduce-scatter
+    by code range, finalize of the owned slice and all-gather in one pass over the blocks of all ranks, which live in
+    a torch symmetric-memory allocation (torch supplies the allocation, the peer pointers and the device-side
+    barrier; the data path is the kernel).  The kernel runs on a side stream between two barriers across the ranks,
+    so the caller's stream is free for the replicated foreground count; finish() then folds locally."""
+
+    name = "k_merge_finalize: fused reduce-scatter + finalize + all-gather over NVLink peer mappings; fold on every rank"
+
+    def __init__(self, words, kmin, kmax, device):
+        import ctypes
+        import torch
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as symm
+        TableMerge.__init__(self, words, kmin, kmax, device)
+        self.lib = _lib.load()
+        self.ctx = _lib.context(device.index)
+        self.world, self.rank = td.get_world_size(), td.get_rank()
+        ok = ctypes.c_int(0)
+        _lib.check(self.lib.swga_merge_supported(kmin, kmax, self.world, ctypes.byref(ok)))
+        if not ok.value:
+            raise NotImplementedError("k_merge_finalize covers kmax - kmin <= 7 on 2, 4 or 8 ranks")
+        try:
+            symm.enable_symm_mem_for_group(td.group.WORLD.group_name)
+        except Exception:
+            pass
+        self.t = symm.empty(words, dtype=torch.int32, device=device)
+        self.hdl = symm.rendezvous(self.t, td.group.WORLD)
+        self.ptrs = np.array([int(p) for p in self.hdl.buffer_ptrs], dtype=np.uint64)
+        assert len(self.ptrs) == self.world and int(self.ptrs[self.rank]) == self.t.data_ptr()
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
+
+    def block(self):
+        return self.t
+
+    def start(self, d_fwd, events=None):
+        import torch
+        assert d_fwd.data_ptr() == self.t.data_ptr(), "accumulate into TableMerge.block()"
+        cur = torch.cuda.current_stream(self.device)
+        self.ev_in.record(cur)
+        self.side.wait_event(self.ev_in)
+        with torch.cuda.stream(self.side):
+            self.hdl.barrier(channel=0)                        # every rank has finished accumulating
+            _lib.check(self.lib.swga_merge_finalize(self.ctx.h, _lib.ptr(self.ptrs), self.world, self.rank, self.kmin,
+                                                    self.kmax, self.side.cuda_stream))
+            self.hdl.barrier(channel=1)                        # every rank has written its slice everywhere
+            self.ev_out.record(self.side)
+
+    def finish(self, d_fwd, d_canon, events=None):
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if events is not None:
+            events[0].record()
+        cur.wait_event(self.ev_out)
+        if events is not None:
+            events[1].record()
+        _lib.check(self.lib.swga_fold_canonical(self.ctx.h, self.kmin, self.kmax, _lib.ptr(d_fwd), _lib.ptr(d_canon),
+                                                cur.cuda_stream))
+
+
+def table_merge(words, kmin, kmax, device, prefer="peer"):
+    """The best merge this job supports: the fused peer-memory kernel, else the NCCL all_reduce."""
+    if prefer == "peer":
+        try:
+            return PeerTableMerge(words, kmin, kmax, device)
+        except Exception as e:                                  # no symmetric memory / no P2P on this box
+            m = TableMerge(words, kmin, kmax, device)
+            m.name += " (peer merge unavailable: %s)" % (repr(e)[:200],)
+            return m
+    return TableMerge(words, kmin, kmax, device)

@@ -492,3 +492,33 @@ def test_full_size_c2_background_vs_oracle(oracle, torch_cuda):
         dt, __import__("os").cpu_count(), stats.tolist(), bad))
     assert bad == 0
     assert int(got[-4 ** 12:].astype(np.int64).sum()) == int(np.maximum(0, np.diff(rs.astype(np.int64)) - 11).sum())
+
+
+@pytest.mark.parametrize("world,kmin,kmax", [(2, 5, 12), (4, 5, 12), (8, 5, 12), (8, 8, 11), (2, 6, 9), (4, 10, 10)])
+def test_merge_finalize_kernel_emulated_ranks(world, kmin, kmax, torch_cuda):
+    """csrc/merge.cu on ONE device: `world` blocks stand for the ranks' additive tables and the per-rank kernels run
+    one after another (rank r sums, finalizes and writes back the slice r / world of every table into all blocks).
+    Afterwards every block must equal swga_count_finalize of the element-wise sum -- the kernel is linear, so
+    arbitrary 32-bit contents (wrapping sums included) are a complete test."""
+    import ctypes
+    torch = torch_cuda
+    from swga_b200 import _lib
+    lib, ctx = _lib.load(), _lib.context(0)
+    ok = ctypes.c_int(0)
+    _lib.check(lib.swga_merge_supported(kmin, kmax, world, ctypes.byref(ok)))
+    assert ok.value == 1
+    words = int(lib.swga_tables_words(kmin, kmax))
+    g = torch.Generator(device="cuda").manual_seed(1234 + world + kmax)
+    blocks = [torch.randint(-2 ** 31, 2 ** 31 - 1, (words,), dtype=torch.int32, device="cuda", generator=g) for _ in range(world)]
+    want = blocks[0].clone()
+    for b in blocks[1:]:
+        want += b
+    _lib.check(lib.swga_count_finalize(ctx.h, kmin, kmax, _lib.ptr(want), None))
+    ptrs = np.array([b.data_ptr() for b in blocks], dtype=np.uint64)
+    for rank in range(world):
+        _lib.check(lib.swga_merge_finalize(ctx.h, _lib.ptr(ptrs), world, rank, kmin, kmax, None))
+    torch.cuda.synchronize()
+    for r, b in enumerate(blocks):
+        assert torch.equal(b, want), (r, int((b != want).sum()))
+    _lib.check(lib.swga_merge_supported(4, 12, world, ctypes.byref(ok)))
+    assert ok.value == 0                                           # more than 7 levels below kmax: not covered
