@@ -18,8 +18,8 @@
 //   (1) k_bucket_hist   counts the prefixes of a strided SAMPLE of the genome (1 warp-tile in `stride`);
 //   (2) k_bucket_layout turns the sample into (a) a global bucket layout -- estimated size + slack per
 //       bucket -- and (b) per-tile slot ranges inside the shared-memory staging area of k_partition;
-//   (3) k_partition     one tile = 32 Ki starts = 16 Ki elements: every element takes its staging slot with
-//       ONE shared atomicAdd on a packed (guard | byte address) counter and ONE 2-byte shared store; the
+//   (3) k_partition     one tile = 64 Ki starts = 32 Ki elements: every element takes its staging slot with
+//       ONE shared atomicAdd on a packed (guard | slot) counter and ONE 2-byte shared store; the
 //       whole 16-byte chunks of every bucket's run are then copied to the bucket (one global atomicAdd per
 //       bucket and tile reserves the range), the up to 7 elements left over wait for the next tile;
 //   (4) k_bucket_count  shared-memory histogram of each bucket, flushed to T_kmax through the two maps.
@@ -35,17 +35,19 @@
 
 #define PT_THREADS 1024                             // one CTA per SM
 #define PT_EPG 16                                   // elements per group of 32 starts (the even offsets)
-#define PT_TILE_STARTS (PT_THREADS * 32)            // 32768 starts per tile, one group of 32 per thread
-#define PT_TILE_ELEMS (PT_THREADS * PT_EPG)         // 16384 elements per tile
+#define PT_GP 2                                     // groups per thread and tile
+#define PT_TILE_STARTS (PT_THREADS * 32 * PT_GP)    // 65536 starts per tile
+#define PT_TILE_ELEMS (PT_THREADS * PT_EPG * PT_GP) // 32768 elements per tile
 #define PT_LB 15                                    // low bits kept per element (uint16), 32768-bin tables
 #define PT_MIN_PB 7                                 // kmax = 10: 2 * 11 - 15
 #define PT_MAX_PB 11                                // kmax = 12: 2 * 13 - 15
-#define PT_STAGE 57344u                             // uint16 staging slots per tile (112 KB)
+#define PT_STAGE 90112u                             // uint16 staging slots per tile (176 KB)
 #define PT_CH 8                                     // bucket runs are stored in whole 16-byte chunks of 8 elements,
 #define PT_PAD_WORD 0x80008000u                     // padded with values 0x8000 | r (r < PT_PAD_BINS), which land in
 #define PT_PAD_BINS 64                              // dump bins behind k_bucket_count's 2^15-bin table
 #define PT_OVF_CAP 512u                             // staging-overflow list entries per tile
-#define PT_ADD ((1u << 17) + 2u)                    // one element: guard += 1, byte address += 2
+#define PT_ADD ((1u << 17) + 1u)                    // one element: guard += 1, slot += 1
+#define PT_CAP_MAX (0x4000u - 8u)                   // slots of one bucket's range (14-bit guard)
 #define PT_ITEMS 2                                  // buckets per thread in the single-block layout kernels (nb <= 2048)
 #define HIST_THREADS 512
 #define BC_THREADS 1024
@@ -109,10 +111,10 @@ __device__ __forceinline__ uint32_t window(const Group &g, int o)
     return o < 16 ? __funnelshift_l(g.w1, g.w0, 2 * o) : __funnelshift_l(g.w2, g.w1, 2 * (o - 16));
 }
 
-// all 32 kmax-mers of the group are the same single-base run
+// the group (and the kmax-1 bases after it) is a repeat of period 1 or 2: all even-offset (kmax+1)-mers are equal
 __device__ __forceinline__ bool uniform_group(const Group &g, int kmax)
 {
-    return g.w0 == g.w1 && g.w0 == __funnelshift_l(g.w0, g.w0, 2) && ((g.w2 ^ g.w0) >> (34 - 2 * kmax)) == 0u;
+    return g.w0 == g.w1 && g.w0 == __funnelshift_l(g.w0, g.w0, 4) && ((g.w2 ^ g.w0) >> (34 - 2 * kmax)) == 0u;
 }
 
 // direct path for a group that touches a break or the end of the owned range (same as k_count's slow path)
@@ -261,7 +263,7 @@ k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n
         cap_t[j] = 0;
         if (b < nb) {
             const unsigned long long share = S ? s[j] * (PT_TILE_ELEMS * 5 / 4) / S : 0ull;
-            cap_t[j] = (min((unsigned long long)PT_TILE_ELEMS, share + beta) + 7ull) & ~7ull;
+            cap_t[j] = min((unsigned long long)PT_CAP_MAX, (share + beta + 7ull) & ~7ull);
         }
     }
     unsigned long long tot_t;
@@ -269,7 +271,7 @@ k_bucket_layout(const uint32_t *__restrict__ sample_cnt, uint32_t nb, uint64_t n
 #pragma unroll
     for (int j = 0; j < PT_ITEMS; ++j) {
         const uint32_t b = PT_ITEMS * threadIdx.x + j;
-        if (b < nb) init[b] = ((0x4000u - (uint32_t)cap_t[j]) << 17) | (uint32_t)(start[j] * 2);
+        if (b < nb) init[b] = ((0x4000u - (uint32_t)cap_t[j]) << 17) | (uint32_t)start[j];
     }
 }
 
@@ -302,11 +304,12 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     constexpr uint32_t NB = 1u << PB, LMASK = (1u << PT_LB) - 1u;
     constexpr int WARPS = PT_THREADS / 32, UNITS = NB / 32;      // a unit = 32 buckets, one per lane
     constexpr int ROUNDS = (UNITS + WARPS - 1) / WARPS;        // units per warp
+    static_assert(NB <= PT_ITEMS * 1024 && (NB % 32) == 0, "bucket count");
     extern __shared__ __align__(16) uint32_t sm[];
-    uint32_t *fill = sm;                                       // [NB] (guard << 17) | byte address of the next slot
+    uint32_t *fill = sm;                                       // [NB] (guard << 17) | next slot of the bucket's range
     uint32_t *init = fill + NB;                                // [NB] value of fill at the start of a tile
     uint32_t *ovf = init + NB;                                 // [PT_OVF_CAP] codes that found their staging range full
-    unsigned char *stg = reinterpret_cast<unsigned char *>(ovf + PT_OVF_CAP);   // [PT_STAGE] uint16
+    uint16_t *stg = reinterpret_cast<uint16_t *>(ovf + PT_OVF_CAP);   // [PT_STAGE]
     __shared__ uint32_t s_novf[2];                             // entries of `ovf`, by tile parity
     __shared__ uint32_t s_stats[4];                            // exits taken: staging full, bucket full, uniform, slow groups
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -333,67 +336,102 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     __syncthreads();
 
     uint32_t par = 0;
-    RawGroup R = prefetch_group(packed, brk, (uint64_t)blockIdx.x * PT_THREADS + tid, n_starts);
-    static_assert(NB <= PT_ITEMS * 1024 && (NB % 32) == 0, "bucket count");
+    // group of (tile, gp, thread): consecutive threads read consecutive groups; the NEXT group's words are always in
+    // flight while the current one is scattered (past the last group: past n_starts, nothing is loaded)
+    const uint64_t n_groups_all = (uint64_t)n_tiles * (PT_THREADS * PT_GP);
+    uint64_t g = (uint64_t)blockIdx.x * (PT_THREADS * PT_GP) + tid;
+    RawGroup R = prefetch_group(packed, brk, g, n_starts);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t g = (uint64_t)tile * PT_THREADS + tid;
-        const Group G = finish_group(R, g, n_starts, KMAX);
-        // next tile's group: in flight during this tile (past the last tile: past n_starts, nothing is loaded)
-        R = prefetch_group(packed, brk, g + (uint64_t)gridDim.x * PT_THREADS, tile + gridDim.x < n_tiles ? n_starts : 0);
-        // ---- every element takes its staging slot ----
-        if (G.fast) {
-            if (uniform_group(G, KMAX)) {
-                atomicAdd(top + (G.w0 >> SH), 32u);
-                atomicAdd(&s_stats[2], 1u);
-            } else {
-                uint32_t full = 0;                             // bit 15-e: element e (offset 2e) found its range full
+#pragma unroll 1
+        for (int gp = 0; gp < PT_GP; ++gp) {
+            const Group G = finish_group(R, g, n_starts, KMAX);
+            const uint64_t g_cur = g;
+            g = gp + 1 < PT_GP ? g + PT_THREADS
+                               : (uint64_t)(tile + gridDim.x) * (PT_THREADS * PT_GP) + tid;
+            R = prefetch_group(packed, brk, g, g < n_groups_all ? n_starts : 0);
+            // ---- every element takes its staging slot ----
+            if (G.fast) {
+                if (uniform_group(G, KMAX)) {                  // poly-A, (AC)n, mode B's N -> G: 16 equal elements
+                    atomicAdd(top + (G.w0 >> SH), 16u);
+                    atomicAdd(top + ((G.w0 >> SHE) & ((1u << (2 * KMAX)) - 1u)), 16u);
+                    atomicAdd(&s_stats[2], 1u);
+                } else {
+                    uint32_t full = 0;                         // bit 15-e: element e (offset 2e) found its range full
+                    uint32_t prev = 0xffffffffu;
 #pragma unroll
-                for (int o = 0; o < 32; o += 2) {
-                    const uint32_t W = window(G, o);
-                    const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
-                    const uint32_t old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
-                    // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on
-                    // a 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
-                    if ((int32_t)old >= 0)
-                        *reinterpret_cast<uint16_t *>(stg + ((old & 0x1FFFFu) ^ ((boff >> 1) & 0xEu))) = (uint16_t)((W >> SHE) & LMASK);
-                    full = __funnelshift_l(old, full, 1);
+                    for (int o = 0; o < 32; o += 2) {
+                        const uint32_t W = window(G, o);
+                        const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
+                        // An element that follows one of the same bucket takes the overflow path: a group then adds at
+                        // most 8 to any counter, a tile at most 2^14, and the 14-bit guard cannot wrap (it would
+                        // re-open a full range after 2^14 + range further elements of one tile).
+                        uint32_t old = 0x80000000u;
+                        if (boff != prev)
+                            old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
+                        prev = boff;
+                        // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on
+                        // a 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
+                        if ((int32_t)old >= 0) stg[(old & 0x1FFFFu) ^ ((boff >> 2) & 7u)] = (uint16_t)((W >> SHE) & LMASK);
+                        full = __funnelshift_l(old, full, 1);
+                    }
+                    while (full) {                             // rare: the tile's composition is off the sample's
+                        const int e = __clz(full) - 16;
+                        full &= ~(0x8000u >> e);
+                        const uint32_t code = window(G, 2 * e) >> SHE;
+                        const uint32_t slot = atomicAdd(&s_novf[par], 1u);
+                        if (slot < PT_OVF_CAP) ovf[slot] = code;
+                        else add_element(top, code, KMAX);     // list full too: straight to the table
+                    }
                 }
-                while (full) {                                 // rare: the tile's composition is off the sample's
-                    const int e = __clz(full) - 16;
-                    full &= ~(0x8000u >> e);
-                    const uint32_t code = window(G, 2 * e) >> SHE;
-                    const uint32_t slot = atomicAdd(&s_novf[par], 1u);
-                    if (slot < PT_OVF_CAP) ovf[slot] = code;
-                    else add_element(top, code, KMAX);         // list full too: straight to the table
-                }
+            } else {
+                slow_group(packed, brk, g_cur, n_starts, kmin, KMAX, tables, offs);
+                if (g_cur * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
             }
-        } else {
-            slow_group(packed, brk, g, n_starts, kmin, KMAX, tables, offs);
-            if (g * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
         }
         __syncthreads();
-        // ---- per warp: reserve the global range of the runs of its buckets, re-arm ----
-        // Only WHOLE chunks of 8 leave the staging area; the up to 7 elements left over stay at the head of the
+        // ---- per warp, lane = bucket: reserve the global range of the run, copy its whole chunks, re-arm ----
+        // Only WHOLE chunks of 8 leave the staging area; the up to 7 elements left over move to the head of the
         // bucket's range for the next tile, so padding is written once per (CTA, bucket), with the last tile.
         const bool last = tile + gridDim.x >= n_tiles;
-        uint32_t A_[ROUNDS], at_[ROUNDS];                      // A = staged | first slot << 15 | does-not-fit << 31
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t unit = r * WARPS + warp;
-            A_[r] = at_[r] = 0;
             if (unit >= UNITS) continue;
             const uint32_t b = unit * 32 + lane;
             const uint32_t f = fill[b], i0 = init[b];
-            const uint32_t u = (int32_t)f < 0 ? 0x4000u - (i0 >> 17) : ((f - i0) & 0x1FFFFu) >> 1;   // elements staged
-            const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;       // elements that leave now
-            uint32_t at = 0, part = 0;
+            const uint32_t cap = 0x4000u - (i0 >> 17);
+            const uint32_t u = (int32_t)f < 0 ? cap : (f - i0) & 0x1FFFFu;      // elements staged
+            const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;               // elements that leave now
+            const uint32_t s0 = i0 & 0x1FFFFu;                                  // first slot of the range
+            uint32_t at = 0, lim = 0;
             if (ru) {
                 at = atomicAdd(cursor + b, ru);
-                part = at + ru > __ldg(base + b + 1);          // beyond the end of the bucket in `data`
+                lim = __ldg(base + b + 1);                     // end of the bucket in `data`
             }
             fill[b] = i0 + (last ? 0u : (u & 7u) * PT_ADD);
-            A_[r] = u | ((i0 & 0x1FFFFu) >> 1) << 15 | part << 31;
-            at_[r] = at;
+            const uint4 *sp = reinterpret_cast<const uint4 *>(stg + s0);
+            for (uint32_t cc = 0; cc < ru; cc += 8u, ++sp) {
+                uint4 v = *sp;
+                if (u - cc < 8u) v = pad_partial_chunk(v, u - cc, b & 7u, padv);   // last tile only
+                if (at + cc + 8u <= lim) {
+                    *reinterpret_cast<uint4 *>(data + at + cc) = v;
+                } else {                                       // the run crosses the end of its bucket: straight to the table
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                        if (e <= LMASK) {
+                            add_element(top, (b << PT_LB) | e, KMAX);
+                            atomicAdd(&s_stats[1], 1u);
+                        }
+                    }
+                }
+            }
+            // the left-over chunk moves to the head of the range (it is read before it is overwritten: same lane)
+            if (!last && (u & 7u) && ru) {
+                uint4 *hp = reinterpret_cast<uint4 *>(stg + s0);
+                *hp = hp[ru >> 3];
+            }
         }
         // staging-overflow list: one chunk per element
         {
@@ -413,60 +451,6 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                 } else {
                     add_element(top, code, KMAX);
                     atomicAdd(&s_stats[1], 1u);
-                }
-            }
-        }
-        // ---- copy the runs: 4 lanes per bucket, one 16-byte chunk per lane and trip ----
-#pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            const uint32_t b0 = (r * WARPS + warp) * 32;
-            if (b0 >= NB) continue;
-#pragma unroll
-            for (int sr = 0; sr < 4; ++sr) {
-                const int k = sr * 8 + (int)(lane >> 2);
-                const uint32_t A = __shfl_sync(0xffffffffu, A_[r], k);
-                const uint32_t at = __shfl_sync(0xffffffffu, at_[r], k);
-                const uint32_t staged = A & 0x7FFFu;
-                const uint32_t u = last ? (staged + 7u) & ~7u : staged & ~7u;          // whole chunks only
-                uint32_t cc = (lane & 3u) * 8u;                // first element of this lane's chunk
-                unsigned char *sp = stg + 2u * ((A >> 15) & 0xFFFFu) + 2u * cc;
-                uint16_t *gp = data + at + cc;
-                if ((int32_t)A >= 0) {
-#pragma unroll 1
-                    for (; cc < u; cc += 32u, sp += 64, gp += 32) {
-                        uint4 v = *reinterpret_cast<const uint4 *>(sp);
-                        if (staged - cc < 8u) v = pad_partial_chunk(v, staged - cc, (b0 + k) & 7u, padv);   // last tile only
-                        *reinterpret_cast<uint4 *>(gp) = v;
-                    }
-                } else {                                       // the run crosses the end of its bucket
-                    const uint32_t l = __ldg(base + b0 + k + 1);
-#pragma unroll 1
-                    for (; cc < u; cc += 32u, sp += 64, gp += 32) {
-                        uint4 v = *reinterpret_cast<const uint4 *>(sp);
-                        if (staged - cc < 8u) v = pad_partial_chunk(v, staged - cc, (b0 + k) & 7u, padv);
-                        if (at + cc + 8u <= l) {
-                            *reinterpret_cast<uint4 *>(gp) = v;
-                        } else {                               // straight to the table
-                            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-                                if (e <= LMASK) {
-                                    add_element(top, ((b0 + k) << PT_LB) | e, KMAX);
-                                    atomicAdd(&s_stats[1], 1u);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            // the left-over chunk of each of my buckets moves to the head of its range
-            __syncwarp();
-            if (!last) {
-                const uint32_t u = A_[r] & 0x7FFFu, whole = u & ~7u;
-                if ((u & 7u) && whole) {
-                    unsigned char *sp = stg + 2u * ((A_[r] >> 15) & 0xFFFFu);
-                    *reinterpret_cast<uint4 *>(sp) = *reinterpret_cast<const uint4 *>(sp + 2u * whole);
                 }
             }
         }
