@@ -46,6 +46,7 @@
 #define PT_PAD_WORD 0x80008000u                     // padded with values 0x8000 | r (r < PT_PAD_BINS), which land in
 #define PT_PAD_BINS 64                              // dump bins behind k_bucket_count's 2^15-bin table
 #define PT_OVF_CAP 512u                             // staging-overflow list entries per tile
+#define PT_AGG 1024u                                // slots of the per-CTA table that aggregates overflow elements by code
 #define PT_ADD ((1u << 17) + 1u)                    // one element: guard += 1, slot += 1
 #define PT_CAP_MAX (0x4000u - 8u)                   // slots of one bucket's range (14-bit guard)
 #define PT_ITEMS 2                                  // buckets per thread in the single-block layout kernels (nb <= 2048)
@@ -309,7 +310,9 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     uint32_t *fill = sm;                                       // [NB] (guard << 17) | next slot of the bucket's range
     uint32_t *init = fill + NB;                                // [NB] value of fill at the start of a tile
     uint32_t *ovf = init + NB;                                 // [PT_OVF_CAP] codes that found their staging range full
-    uint16_t *stg = reinterpret_cast<uint16_t *>(ovf + PT_OVF_CAP);   // [PT_STAGE]
+    uint32_t *agg_key = ovf + PT_OVF_CAP;                      // [PT_AGG] code of an aggregated overflow element, ~0 = free
+    uint32_t *agg_cnt = agg_key + PT_AGG;                      // [PT_AGG] its multiplicity in this tile
+    uint16_t *stg = reinterpret_cast<uint16_t *>(agg_cnt + PT_AGG);   // [PT_STAGE]
     __shared__ uint32_t s_novf[2];                             // entries of `ovf`, by tile parity
     __shared__ uint32_t s_stats[4];                            // exits taken: staging full, bucket full, uniform, slow groups
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -331,6 +334,10 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
         const uint32_t v = init_g[i];
         init[i] = v;
         fill[i] = v;
+    }
+    for (uint32_t i = tid; i < PT_AGG; i += PT_THREADS) {
+        agg_key[i] = 0xffffffffu;
+        agg_cnt[i] = 0;
     }
     if (tid < 2) s_novf[tid] = 0;
     __syncthreads();
@@ -378,9 +385,29 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                         const int e = __clz(full) - 16;
                         full &= ~(0x8000u >> e);
                         const uint32_t code = window(G, 2 * e) >> SHE;
-                        const uint32_t slot = atomicAdd(&s_novf[par], 1u);
-                        if (slot < PT_OVF_CAP) ovf[slot] = code;
-                        else add_element(top, code, KMAX);     // list full too: straight to the table
+                        // Overflow elements are mostly REPEATS (a tandem repeat puts a whole tile into a few buckets):
+                        // aggregate them by code in a small open-addressing table, flushed once per tile with two
+                        // table updates per DISTINCT code -- per-element red.global on a handful of addresses
+                        // serialises in L2 (measured: a 10x slower genome).  Two probes, then the list, then direct.
+                        uint32_t h = (code * 2654435761u) >> 22;
+                        bool done = false;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            if (!done) {
+                                const uint32_t k = atomicCAS(&agg_key[h], 0xffffffffu, code);
+                                if (k == 0xffffffffu || k == code) {
+                                    atomicAdd(&agg_cnt[h], 1u);
+                                    done = true;
+                                }
+                                h = (h + 1u) & (PT_AGG - 1u);
+                            }
+                        }
+                        if (!done) {
+                            const uint32_t slot = atomicAdd(&s_novf[par], 1u);
+                            if (slot < PT_OVF_CAP) ovf[slot] = code;
+                            else add_element(top, code, KMAX); // list full too: straight to the table
+                        }
+                        atomicAdd(&s_stats[0], 1u);
                     }
                 }
             } else {
@@ -438,8 +465,18 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
             const uint32_t n_all = s_novf[par], n_ovf = min(n_all, PT_OVF_CAP);
             if (tid == 0) {
                 s_novf[par ^ 1] = 0;
-                s_stats[0] += n_all;
                 if (n_all > n_ovf) s_stats[1] += n_all - n_ovf;
+            }
+            // aggregated overflow elements: both k-mers of each distinct code, with its multiplicity
+            for (uint32_t i = tid; i < PT_AGG; i += PT_THREADS) {
+                const uint32_t code = agg_key[i];
+                if (code != 0xffffffffu) {
+                    const uint32_t c = agg_cnt[i];
+                    atomicAdd(top + (code >> 2), c);
+                    atomicAdd(top + (code & ((1u << (2 * KMAX)) - 1u)), c);
+                    agg_key[i] = 0xffffffffu;
+                    agg_cnt[i] = 0;
+                }
             }
             for (uint32_t i = tid; i < n_ovf; i += PT_THREADS) {
                 const uint32_t code = ovf[i], b = code >> PT_LB;
@@ -613,7 +650,7 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
     SWGA_NOTE_LAUNCH(); k_bucket_hist<<<grid_h, HIST_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
     SWGA_NOTE_LAUNCH(); k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
     if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[1], stream));
-    const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_STAGE * 2;
+    const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_AGG * 8 + PT_STAGE * 2;
     const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
 #define LAUNCH_PARTITION(K)                                                                                              \
     do {                                                                                                                 \
