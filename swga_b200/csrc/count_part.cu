@@ -420,47 +420,28 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
         // Only WHOLE chunks of 8 leave the staging area; the up to 7 elements left over move to the head of the
         // bucket's range for the next tile, so padding is written once per (CTA, bucket), with the last tile.
         const bool last = tile + gridDim.x >= n_tiles;
+        // pass A: the reservations of ALL my buckets are in flight together (a global atomic with a result is a
+        // ~2 us round trip here; the profile showed the write-out waiting for them one round at a time)
+        uint32_t u_[ROUNDS], s0_[ROUNDS], at_[ROUNDS], lim_[ROUNDS];
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t unit = r * WARPS + warp;
+            u_[r] = s0_[r] = at_[r] = lim_[r] = 0;
             if (unit >= UNITS) continue;
             const uint32_t b = unit * 32 + lane;
             const uint32_t f = fill[b], i0 = init[b];
             const uint32_t cap = 0x4000u - (i0 >> 17);
             const uint32_t u = (int32_t)f < 0 ? cap : (f - i0) & 0x1FFFFu;      // elements staged
             const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;               // elements that leave now
-            const uint32_t s0 = i0 & 0x1FFFFu;                                  // first slot of the range
-            uint32_t at = 0, lim = 0;
             if (ru) {
-                at = atomicAdd(cursor + b, ru);
-                lim = __ldg(base + b + 1);                     // end of the bucket in `data`
+                at_[r] = atomicAdd(cursor + b, ru);
+                lim_[r] = __ldg(base + b + 1);                 // end of the bucket in `data`
             }
             fill[b] = i0 + (last ? 0u : (u & 7u) * PT_ADD);
-            const uint4 *sp = reinterpret_cast<const uint4 *>(stg + s0);
-            for (uint32_t cc = 0; cc < ru; cc += 8u, ++sp) {
-                uint4 v = *sp;
-                if (u - cc < 8u) v = pad_partial_chunk(v, u - cc, b & 7u, padv);   // last tile only
-                if (at + cc + 8u <= lim) {
-                    *reinterpret_cast<uint4 *>(data + at + cc) = v;
-                } else {                                       // the run crosses the end of its bucket: straight to the table
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-                        if (e <= LMASK) {
-                            add_element(top, (b << PT_LB) | e, KMAX);
-                            atomicAdd(&s_stats[1], 1u);
-                        }
-                    }
-                }
-            }
-            // the left-over chunk moves to the head of the range (it is read before it is overwritten: same lane)
-            if (!last && (u & 7u) && ru) {
-                uint4 *hp = reinterpret_cast<uint4 *>(stg + s0);
-                *hp = hp[ru >> 3];
-            }
+            u_[r] = u;
+            s0_[r] = i0 & 0x1FFFFu;                            // first slot of the range
         }
-        // staging-overflow list: one chunk per element
+        // (while the reservations are in flight) staging-overflow list: one chunk per element
         {
             const uint32_t n_all = s_novf[par], n_ovf = min(n_all, PT_OVF_CAP);
             if (tid == 0) {
@@ -489,6 +470,38 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                     add_element(top, code, KMAX);
                     atomicAdd(&s_stats[1], 1u);
                 }
+            }
+        }
+        // pass B: copy the whole chunks, move the left-over chunk to the head of the range
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t unit = r * WARPS + warp;
+            if (unit >= UNITS) continue;
+            const uint32_t b = unit * 32 + lane;
+            const uint32_t u = u_[r], at = at_[r], lim = lim_[r];
+            const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;
+            const uint4 *sp = reinterpret_cast<const uint4 *>(stg + s0_[r]);
+            for (uint32_t cc = 0; cc < ru; cc += 8u, ++sp) {
+                uint4 v = *sp;
+                if (u - cc < 8u) v = pad_partial_chunk(v, u - cc, b & 7u, padv);   // last tile only
+                if (at + cc + 8u <= lim) {
+                    *reinterpret_cast<uint4 *>(data + at + cc) = v;
+                } else {                                       // the run crosses the end of its bucket: straight to the table
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                        if (e <= LMASK) {
+                            add_element(top, (b << PT_LB) | e, KMAX);
+                            atomicAdd(&s_stats[1], 1u);
+                        }
+                    }
+                }
+            }
+            // the left-over chunk moves to the head of the range (it is read before it is overwritten: same lane)
+            if (!last && (u & 7u) && ru) {
+                uint4 *hp = reinterpret_cast<uint4 *>(stg + s0_[r]);
+                *hp = hp[ru >> 3];
             }
         }
         __syncthreads();
