@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
     ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
                     help="cross-GPU merge: the fused peer-memory kernel (default) or NCCL all_reduce + finalize on every rank")
+    ap.add_argument("--via-pack", action="store_true", help="A/B: k_pack + partitioned kernels on its output (round-1 data flow)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -309,6 +310,8 @@ def run_b200_arm(args):
             os.close(saved)
     lib, ctx = _lib.load(), _lib.context(local)
     P = _lib.ptr
+    if args.via_pack:
+        _lib.check(lib.swga_ctx_set_count_via_pack(ctx.h, 1))
     words = int(lib.swga_tables_words(KMIN, KMAX))
     merge = dist.table_merge(words, KMIN, KMAX, dev, prefer=args.merge) if world > 1 else None
 
@@ -350,12 +353,13 @@ def run_b200_arm(args):
         def accumulate(self, ev=None):
             """zero + pack + mark + swga_count_accumulate: this rank's additive table block"""
             _lib.check(lib.swga_memset(ctx.h, P(self.fwd), 0, words * 4, None))
-            _lib.check(lib.swga_pack(ctx.h, P(self.ascii), self.n, 0 if self.mode_b else 1, P(self.packed), P(self.brk), None))
-            if len(self.rs) > 2:
-                _lib.check(lib.swga_mark_records(ctx.h, P(self.d_rs[1:]), len(self.rs) - 2, self.n, P(self.brk), None))
             if ev is not None:
                 ev[0].record()
-            _lib.check(lib.swga_count_accumulate(ctx.h, P(self.packed), P(self.brk), self.n_starts, KMIN, KMAX, P(self.fwd), None))
+            # ASCII bases in: the partitioned kernels pack them in registers (no pack pass); small genomes: k_pack + k_count
+            n_marks = len(self.rs) - 2
+            _lib.check(lib.swga_count_accumulate_ascii(ctx.h, P(self.ascii), self.n, P(self.d_rs[1:]) if n_marks else None, n_marks,
+                                                       0 if self.mode_b else 1, self.n_starts, KMIN, KMAX, P(self.packed),
+                                                       P(self.brk), P(self.fwd), None))
             if ev is not None:
                 ev[1].record()
 
@@ -452,9 +456,10 @@ def run_b200_arm(args):
         6650.0, "fallback of B200_PROFILING.md")
     tr = load_json("profiles", "r02_count_stage_traffic.json") or load_json("profiles", "r01_count_stage_traffic.json")
     if partitioned:
-        # k_partition reads the packed genome once: 1/4 B per base (+ 1/32 B of break mask); the bucket elements it
-        # writes are this implementation's own intermediate, counted under `traffic`, not here
-        k_bytes = (0.25 + 1.0 / 32.0) * bg.n_starts
+        # k_partition reads the genome once: 1 B per base of ASCII (+ 1/32 B of break mask) -- SURVEY 8(d)'s "ASCII in";
+        # with --via-pack 1/4 B per base of packed genome.  The bucket elements it writes are this implementation's
+        # own intermediate, counted under `traffic`, not here
+        k_bytes = ((0.25 if args.via_pack else 1.0) + 1.0 / 32.0) * bg.n_starts
         k_ms, k_name = part_ms, "k_partition"
         k_traffic = tr.get("k_partition_dram_bytes_per_base")
         smem_ops = 0.5                                        # slot atomics per base: one per element = per two bases
@@ -463,7 +468,7 @@ def run_b200_arm(args):
         k_ms, k_name = count_ms, "k_count"
         k_traffic, smem_ops = None, 0.0
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
-    stage_bytes = 0.25 * bg.n_starts + 4.0 * 4 ** KMAX         # packed genome read once + top table written once
+    stage_bytes = (0.25 if args.via_pack else 1.0) * bg.n_starts + 4.0 * 4 ** KMAX     # genome read once + top table written once
     stage_ops = 1.0                                            # shared atomics per base, whole stage: slot + histogram bin per element
     roofline = {
         "kernel": k_name, "bound": "smem" if partitioned else "l2_atomic",

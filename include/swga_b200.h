@@ -121,6 +121,17 @@ int swga_mark_records(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64_t n_re
  * swga_fold_canonical writes DSK's canonical counts (Kmer.cpp:122: min(fwd, revcomp)):
  *   C_k[x] = T_k[x] + T_k[rc(x)] if x < rc(x);  T_k[x] if x == rc(x);  0 otherwise.
  */
+/* The same accumulate fed with the ASCII bases (device-resident, 16-byte aligned): for inputs large enough for
+ * the partitioned kernels they read the bases themselves and pack them in registers -- no pack pass over the
+ * genome (its 1 + 1/4 + 1/8 bytes per base of DRAM traffic and 0.6 ms per 3.1 Gbp are gone); smaller inputs are
+ * packed into d_packed / d_brk (workspaces of swga_packed_words(n) / swga_brk_words(n) words, always overwritten)
+ * and take the direct kernel.  d_rec_marks: device array of the n_marks record starts s with 0 < s <= n (the
+ * boundaries inside the buffer), may be NULL.  mask_mode: SWGA_MASK_NONE (DSK mode B) or SWGA_MASK_N (mode A).
+ * swga_ctx_set_count_via_pack(ctx, 1) makes the partitioned kernels read k_pack's output instead (A/B timing). */
+int swga_count_accumulate_ascii(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, const uint64_t *d_rec_marks,
+                                uint64_t n_marks, int mask_mode, uint64_t n_starts, int kmin, int kmax,
+                                uint32_t *d_packed, uint32_t *d_brk, uint32_t *d_tables, void *stream);
+int swga_ctx_set_count_via_pack(swga_ctx *ctx, int on);
 int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk,
                           uint64_t n_starts, int kmin, int kmax, uint32_t *d_tables, void *stream);
 int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *d_tables, void *stream);
@@ -139,7 +150,7 @@ int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd
                         uint32_t *d_canon, void *stream);
 
 /* The cross-GPU merge of the ranks' additive blocks fused with swga_count_finalize (csrc/merge.cu): h_blocks holds
- * `world` (2, 4 or 8) device pointers -- this rank's peer mappings of every rank's block, in rank order, e.g. the
+ * `world` (1, 2, 4 or 8) device pointers -- this rank's peer mappings of every rank's block, in rank order, e.g. the
  * buffer_ptrs of a torch symmetric-memory allocation.  Rank r sums, finalizes and writes back, into ALL blocks,
  * the slice [r, r + 1) / world of every table; when all ranks have run it (the caller puts a barrier across the
  * ranks before and after), every block holds the finalized forward tables of the whole genome.  Needs

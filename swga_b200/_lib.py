@@ -42,6 +42,9 @@ SIGNATURES = {
     "swga_mark_records": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp]),
     "swga_count_accumulate": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                              c_vp, c_vp]),
+    "swga_count_accumulate_ascii": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,
+                                                   ctypes.c_uint64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    "swga_ctx_set_count_via_pack": (ctypes.c_int, [c_ctx, ctypes.c_int]),
     "swga_count_partition_stats": (ctypes.c_int, [c_ctx, c_u64p]),
     "swga_ctx_set_stage_timing": (ctypes.c_int, [c_ctx, ctypes.c_int]),
     "swga_count_stage_ms": (ctypes.c_int, [c_ctx, ctypes.POINTER(ctypes.c_float)]),

@@ -112,6 +112,12 @@ extern "C" int swga_ctx_set_count_impl(swga_ctx *c, int impl)
     c->count_impl = impl;
     return SWGA_OK;
 }
+extern "C" int swga_ctx_set_count_via_pack(swga_ctx *c, int on)
+{
+    ARG_CHECK(c);
+    c->count_via_pack = on ? 1 : 0;
+    return SWGA_OK;
+}
 
 int swga_ensure(swga_ctx *ctx, DevBuf &b, size_t bytes)
 {
@@ -474,9 +480,8 @@ extern "C" int swga_count_genome_device(swga_ctx *ctx, const uint8_t *d_ascii, u
     }
     uint32_t *packed = (uint32_t *)ctx->packed.p, *brk = (uint32_t *)ctx->brk.p;
     CUDA_TRY(cudaMemsetAsync(d_fwd, 0, words * 4, as_stream(stream)));
-    TRY(swga_pack(ctx, d_ascii, n, mask_mode, packed, brk, stream));
-    if (n_rec > 1) TRY(swga_mark_records(ctx, d_rec_starts + 1, n_rec - 1, n, brk, stream));
-    TRY(swga_count_accumulate(ctx, packed, brk, n_starts, kmin, kmax, d_fwd, stream));
+    TRY(swga_count_ascii(ctx, d_ascii, n, n_rec > 1 ? d_rec_starts + 1 : nullptr, n_rec > 1 ? n_rec - 1 : 0, 0, mask_mode,
+                         n_starts, kmin, kmax, packed, brk, d_fwd, as_stream(stream)));
     if (finalize) {
         TRY(swga_count_finalize(ctx, kmin, kmax, d_fwd, stream));
         TRY(swga_fold_canonical(ctx, kmin, kmax, d_fwd, d_canon, stream));
@@ -495,16 +500,19 @@ static int enqueue_chunk(swga_ctx *ctx, int b, const uint8_t *src, uint64_t len,
     CUDA_TRY(cudaEventRecord(ctx->ev_h2d[b], ctx->s_copy));
     CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
     uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
-    TRY(swga_pack(ctx, (const uint8_t *)ctx->ascii[b].p, len, mask_mode, packed, brk, ctx->s_comp));
+    const uint64_t *marks = nullptr;
+    uint64_t n_marks = 0;
     if (n_rec > 1) {
         // records whose start s satisfies origin < s <= origin + len
         const uint64_t *lo = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, origin);
         const uint64_t *hi = std::upper_bound(h_rec_starts + 1, h_rec_starts + n_rec, origin + len);
-        if (hi > lo)
-            TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p + (lo - h_rec_starts), (uint64_t)(hi - lo),
-                                         origin, len, brk, ctx->s_comp));
+        if (hi > lo) {
+            marks = (const uint64_t *)ctx->recs.p + (lo - h_rec_starts);
+            n_marks = (uint64_t)(hi - lo);
+        }
     }
-    TRY(swga_count_accumulate(ctx, packed, brk, owned, kmin, kmax, d_fwd, ctx->s_comp));
+    TRY(swga_count_ascii(ctx, (const uint8_t *)ctx->ascii[b].p, len, marks, n_marks, origin, mask_mode, owned, kmin, kmax,
+                         packed, brk, d_fwd, ctx->s_comp));
     CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
     return SWGA_OK;
 }
@@ -878,7 +886,6 @@ static int count_fasta_stream_impl(swga_ctx *ctx, const uint8_t *f, uint64_t n_f
         if (owned > 0) {
             CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_h2d[b], 0));
             uint32_t *packed = (uint32_t *)ctx->packed2[b].p, *brk = (uint32_t *)ctx->brk2[b].p;
-            TRY(swga_pack(ctx, dst, len, mask_mode, packed, brk, ctx->s_comp));
             // record boundaries inside the chunk: starts s with origin < s <= origin + len (the first record never marks)
             const uint64_t *lo = std::upper_bound(rs.data(), rs.data() + rs.size(), origin);
             const uint64_t *hi = std::upper_bound(rs.data(), rs.data() + rs.size(), origin + len);
@@ -889,10 +896,9 @@ static int count_fasta_stream_impl(swga_ctx *ctx, const uint8_t *f, uint64_t n_f
                 memcpy(ctx->h_recs[b], lo, bytes);
                 TRY(swga_ensure(ctx, ctx->recs, bytes));
                 CUDA_TRY(cudaMemcpyAsync(ctx->recs.p, ctx->h_recs[b], bytes, cudaMemcpyHostToDevice, ctx->s_comp));
-                TRY(swga_mark_records_origin(ctx, (const uint64_t *)ctx->recs.p, (uint64_t)(hi - lo), origin, len, brk,
-                                             ctx->s_comp));
             }
-            TRY(swga_count_accumulate(ctx, packed, brk, owned, kmin, kmax, d_fwd, ctx->s_comp));
+            TRY(swga_count_ascii(ctx, dst, len, hi > lo ? (const uint64_t *)ctx->recs.p : nullptr, (uint64_t)(hi - lo), origin,
+                                 mask_mode, owned, kmin, kmax, packed, brk, d_fwd, ctx->s_comp));
             CUDA_TRY(cudaEventRecord(ctx->ev_done[b], ctx->s_comp));
         }
         t_wait += tb - ta;

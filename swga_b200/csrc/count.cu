@@ -16,27 +16,6 @@
 // ------------------------------------------------------------------------------------------------
 // (a) pack: one thread = 32 bases = two 128-bit loads -> one uint2 packed store + one brk word.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t codes4(uint32_t w)
-{
-    // 4 ASCII bytes (first base in the low byte) -> 8 bits, first base in bits 7:6.
-    // (c>>1)&3 per byte, then one multiply gathers the four 2-bit fields (no carries: the partial
-    // products land on disjoint bit positions).
-    uint32_t x = (w >> 1) & 0x03030303u;
-    return (x * ((1u << 30) | (1u << 20) | (1u << 10) | 1u)) >> 24;
-}
-__device__ __forceinline__ uint32_t flags4(uint32_t m)
-{
-    // m has 0x01 in each flagged byte (first base in the low byte) -> 4 bits, first base in bit 3.
-    return (m * ((1u << 31) | (1u << 22) | (1u << 13) | (1u << 4))) >> 28;
-}
-__device__ __forceinline__ uint32_t bad4(uint32_t w, int mask_mode)
-{
-    if (mask_mode == SWGA_MASK_N) return __vcmpeq4(w, 0x4E4E4E4Eu) & 0x01010101u;   // 'N'
-    uint32_t ok = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) |            // A C
-                  __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);             // G T
-    return ~ok & 0x01010101u;
-}
-
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ ascii, uint64_t n, int mask_mode,
        uint32_t *__restrict__ packed, uint32_t *__restrict__ brk, uint64_t n_groups)
@@ -303,10 +282,12 @@ k_bench_atom_shared(uint32_t mask, uint64_t ops_per_thread, uint32_t *__restrict
     if (threadIdx.x == 0) atomicAdd(sink, sh[0]);
 }
 
+
+
 #define PT_AUTO_MIN_STARTS (14ull << 20)                    // auto mode: partitioned path from here on
 
-int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n_starts,
-                                      int kmin, int kmax, uint32_t *d_tables, cudaStream_t stream, int *done);
+int swga_mark_records_origin(swga_ctx *ctx, const uint64_t *d_rec_starts, uint64_t n_rec, uint64_t origin,
+                             uint64_t n, uint32_t *d_brk, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // C ABI wrappers
@@ -389,7 +370,11 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     // are limited by the per-SM LSU issue path -- profiles/r01_summary.md.)
     if (ctx->count_impl == 2 || (ctx->count_impl == 0 && n_starts >= PT_AUTO_MIN_STARTS)) {
         int done = 0;
-        TRY(swga_count_accumulate_partitioned(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, st, &done));
+        GenomeSrc src;
+        memset(&src, 0, sizeof(src));
+        src.packed = d_packed;
+        src.brk = d_brk;
+        TRY(swga_count_accumulate_partitioned(ctx, src, SRC_PACKED, n_starts, kmin, kmax, d_tables, st, &done));
         if (done) return SWGA_OK;
         if (ctx->count_impl == 2) {
             swga_set_error("partitioned counting does not cover kmax=%d n_starts=%llu", kmax, (unsigned long long)n_starts);
@@ -403,10 +388,67 @@ extern "C" int swga_count_accumulate(swga_ctx *ctx, const uint32_t *d_packed, co
     return SWGA_OK;
 }
 
+// the end-of-buffer break of a mask that holds only record boundaries (the ASCII-fed counting path; k_pack sets it itself)
+__global__ void k_mark_end(uint64_t n, uint32_t *__restrict__ brk)
+{
+    if (n > 0) atomicOr(&brk[(n - 1) >> 5], 1u << (31 - (uint32_t)((n - 1) & 31)));
+}
+
+int swga_count_ascii(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, const uint64_t *d_marks, uint64_t n_marks,
+                     uint64_t origin, int mask_mode, uint64_t n_starts, int kmin, int kmax, uint32_t *d_packed,
+                     uint32_t *d_brk, uint32_t *d_tables, cudaStream_t stream)
+{
+    ARG_CHECK(ctx && (d_ascii || n == 0) && d_packed && d_brk && d_tables && n_starts <= n);
+    ARG_CHECK(mask_mode == SWGA_MASK_NONE || mask_mode == SWGA_MASK_N);
+    ARG_CHECK((reinterpret_cast<uintptr_t>(d_ascii) & 15) == 0);
+    TRY(check_k(kmin, kmax));
+    if (n_starts == 0) return SWGA_OK;
+    // The partitioned kernels read the ASCII bases themselves (packed in registers on the way in): no pack pass, no
+    // packed copy of the genome.  Smaller inputs / other k ranges: pack, then the direct kernel.
+    int part = 0;
+    if (ctx->count_impl == 2 || (ctx->count_impl == 0 && n_starts >= PT_AUTO_MIN_STARTS)) TRY(swga_count_partition_supported(n_starts, kmax, &part));
+    if (part && !ctx->count_via_pack) {
+        CUDA_TRY(cudaMemsetAsync(d_brk, 0, swga_brk_words(n) * 4, stream));
+        SWGA_NOTE_LAUNCH(); k_mark_end<<<1, 1, 0, stream>>>(n, d_brk);
+        TRY(swga_mark_records_origin(ctx, d_marks, n_marks, origin, n, d_brk, stream));
+        GenomeSrc src;
+        memset(&src, 0, sizeof(src));
+        src.brk = d_brk;
+        src.ascii = d_ascii;
+        src.n = n;
+        int done = 0;
+        TRY(swga_count_accumulate_partitioned(ctx, src, mask_mode == SWGA_MASK_N ? SRC_ASCII_N : SRC_ASCII, n_starts, kmin, kmax,
+                                              d_tables, stream, &done));
+        if (done) return SWGA_OK;
+    }
+    TRY(swga_pack(ctx, d_ascii, n, mask_mode, d_packed, d_brk, stream));
+    TRY(swga_mark_records_origin(ctx, d_marks, n_marks, origin, n, d_brk, stream));
+    return swga_count_accumulate(ctx, d_packed, d_brk, n_starts, kmin, kmax, d_tables, stream);
+}
+
+extern "C" int swga_count_accumulate_ascii(swga_ctx *ctx, const uint8_t *d_ascii, uint64_t n, const uint64_t *d_rec_marks,
+                                           uint64_t n_marks, int mask_mode, uint64_t n_starts, int kmin, int kmax,
+                                           uint32_t *d_packed, uint32_t *d_brk, uint32_t *d_tables, void *stream)
+{
+    return swga_count_ascii(ctx, d_ascii, n, d_rec_marks, n_marks, 0, mask_mode, n_starts, kmin, kmax, d_packed, d_brk, d_tables,
+                            as_stream(stream));
+}
+
+extern "C" int swga_merge_supported(int kmin, int kmax, int world, int *ok);
+extern "C" int swga_merge_finalize(swga_ctx *ctx, const uint64_t *h_blocks, int world, int rank, int kmin, int kmax, void *stream);
+
 extern "C" int swga_count_finalize(swga_ctx *ctx, int kmin, int kmax, uint32_t *d_tables, void *stream)
 {
     ARG_CHECK(ctx && d_tables);
     TRY(check_k(kmin, kmax));
+    // up to 7 levels below kmax (the default 5..12): ONE pass over the block (csrc/merge.cu with a single "rank"): every
+    // CTA takes a span of T_kmax and walks its four-way sums down the levels in shared memory
+    int fused = 0;
+    TRY(swga_merge_supported(kmin, kmax, 1, &fused));
+    if (fused && kmax > kmin && (reinterpret_cast<uintptr_t>(d_tables) & 15) == 0) {
+        const uint64_t blk = reinterpret_cast<uint64_t>(d_tables);
+        return swga_merge_finalize(ctx, &blk, 1, 0, kmin, kmax, stream);
+    }
     const TableOffs o = swga_make_offs(kmin, kmax);
     for (int k = kmax - 1; k >= kmin; --k) {
         const uint64_t n_lower = 1ull << (2 * k);

@@ -54,56 +54,115 @@
 #define BC_THREADS 1024
 #define BC_ITEM (1u << 20)                          // elements per work item of k_bucket_count
 
+// Where the bases of a group of 32 starts come from: the packed genome + break mask that k_pack wrote (SRC_PACKED),
+// or the ASCII bases themselves (SRC_ASCII / SRC_ASCII_N: packed in registers on the way in, so that the pack kernel
+// and its 1 + 1/4 + 1/8 bytes per base of DRAM traffic disappear from the counting path; `brk` then holds only the
+// record boundaries and the end of the buffer, and SRC_ASCII_N adds DSK mode A's 'N' breaks on the fly).
 struct Group {
-    uint32_t w0, w1, w2;
+    uint32_t w0, w1, w2;           // bases 0..15, 16..31 of the group and the 16 after it
+    uint32_t b0, b1;               // break bits of the group and of the 32 bases after it
     bool fast;
 };
 
-__device__ __forceinline__ Group load_group(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
-                                            uint64_t g, uint64_t n_starts, int kmax)
+// The raw words of a group, fetched ahead of their use.  Volatile asm loads: the compiler may neither sink them to
+// the first use nor re-issue them there (a plain __ldg of read-only data is rematerialised, which turns a prefetch
+// into a stall); nothing is computed from the values until finish_group().
+template <int SRC> struct RawGroup;
+template <> struct RawGroup<SRC_PACKED> {
+    uint32_t w0, w1, w2, b0, b1;
+};
+struct RawAscii {
+    uint4 a, b, c;                 // bases 0..15, 16..31, 32..47
+    uint32_t b0, b1;
+};
+template <> struct RawGroup<SRC_ASCII> : RawAscii {};
+template <> struct RawGroup<SRC_ASCII_N> : RawAscii {};
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
 {
-    Group r;
-    r.fast = false;
-    r.w0 = r.w1 = r.w2 = 0;
-    const uint64_t p0 = g * 32;
-    if (p0 >= n_starts) return r;
-    const uint2 w01 = __ldg(reinterpret_cast<const uint2 *>(packed) + g);
-    r.w0 = w01.x; r.w1 = w01.y;
-    r.w2 = __ldg(packed + 2 * g + 2);
-    const uint32_t b0 = __ldg(brk + g), b1 = __ldg(brk + g + 1);
-    const int need = kmax - 2;
-    const uint32_t tail = need > 0 ? (b1 >> (32 - need)) : 0u;
-    r.fast = (p0 + 32 <= n_starts) && ((b0 | tail) == 0u);
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const void *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// 16 bases from byte p on, 'A' past the end of the buffer (the break mask ends the last window before them)
+__device__ __forceinline__ uint4 ascii16_edge(const uint8_t *__restrict__ ascii, uint64_t p, uint64_t n)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t q = p + 4 * i + j;
+            v |= (q < n ? (uint32_t)ascii[q] : 0x41u) << (8 * j);
+        }
+        w[i] = v;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int SRC>
+__device__ __forceinline__ RawGroup<SRC> prefetch_group(const GenomeSrc &S, uint64_t g, uint64_t n_starts)
+{
+    RawGroup<SRC> r;
+    r.b0 = r.b1 = 0xffffffffu;
+    if constexpr (SRC == SRC_PACKED) {
+        r.w0 = r.w1 = r.w2 = 0;
+        if (g * 32 >= n_starts) return r;
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(S.packed + 2 * g));
+        r.w2 = ldg_nc_u32(S.packed + 2 * g + 2);
+    } else {
+        r.a = r.b = r.c = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        if (g * 32 >= n_starts) return r;
+        const uint64_t p = g * 32;
+        if (p + 48 <= S.n) {
+            r.a = ldg_nc_v4(S.ascii + p);
+            r.b = ldg_nc_v4(S.ascii + p + 16);
+            r.c = ldg_nc_v4(S.ascii + p + 32);
+        } else {                                               // the last groups of the buffer
+            r.a = ascii16_edge(S.ascii, p, S.n);
+            r.b = ascii16_edge(S.ascii, p + 16, S.n);
+            r.c = ascii16_edge(S.ascii, p + 32, S.n);
+        }
+    }
+    r.b0 = ldg_nc_u32(S.brk + g);
+    r.b1 = ldg_nc_u32(S.brk + g + 1);
     return r;
 }
 
-// The group of the NEXT tile, fetched a whole tile ahead.  Volatile asm loads: the compiler may neither sink
-// them to the first use nor re-issue them there (a plain __ldg of read-only data is rematerialised, which
-// turns a prefetch into a stall); nothing is computed from the values until finish_group().
-struct RawGroup {
-    uint32_t w0, w1, w2, b0, b1;
-};
-__device__ __forceinline__ RawGroup prefetch_group(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
-                                                   uint64_t g, uint64_t n_starts)
-{
-    RawGroup r;
-    r.w0 = r.w1 = r.w2 = 0;
-    r.b0 = r.b1 = 0xffffffffu;
-    if (g * 32 >= n_starts) return r;
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(packed + 2 * g));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.w2) : "l"(packed + 2 * g + 2));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.b0) : "l"(brk + g));
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r.b1) : "l"(brk + g + 1));
-    return r;
-}
-__device__ __forceinline__ Group finish_group(const RawGroup &r, uint64_t g, uint64_t n_starts, int kmax)
+template <int SRC>
+__device__ __forceinline__ Group finish_group(const RawGroup<SRC> &r, uint64_t g, uint64_t n_starts, int kmax)
 {
     Group G;
-    G.w0 = r.w0; G.w1 = r.w1; G.w2 = r.w2;
+    G.b0 = r.b0; G.b1 = r.b1;
+    if constexpr (SRC == SRC_PACKED) {
+        G.w0 = r.w0; G.w1 = r.w1; G.w2 = r.w2;
+    } else {
+        G.w0 = pack16(r.a); G.w1 = pack16(r.b); G.w2 = pack16(r.c);
+        if constexpr (SRC == SRC_ASCII_N) {
+            // an 'N' at base i forbids the windows over (i-1, i) and (i, i+1): brk[j] = bad[j] | bad[j+1]  (k_pack)
+            const uint32_t badA = (flags16(r.a, SWGA_MASK_N) << 16) | flags16(r.b, SWGA_MASK_N);
+            const uint32_t badC = flags16(r.c, SWGA_MASK_N) << 16;
+            G.b0 |= badA | (badA << 1) | (badC >> 31);
+            G.b1 |= badC | (badC << 1);                        // only its leading kmax-2 bits are looked at
+        }
+    }
     const int need = kmax - 2;
-    const uint32_t tail = need > 0 ? (r.b1 >> (32 - need)) : 0u;
-    G.fast = (g * 32 + 32 <= n_starts) && ((r.b0 | tail) == 0u);
+    const uint32_t tail = need > 0 ? (G.b1 >> (32 - need)) : 0u;
+    G.fast = (g * 32 + 32 <= n_starts) && ((G.b0 | tail) == 0u);
     return G;
+}
+
+template <int SRC>
+__device__ __forceinline__ Group load_group(const GenomeSrc &S, uint64_t g, uint64_t n_starts, int kmax)
+{
+    return finish_group<SRC>(prefetch_group<SRC>(S, g, n_starts), g, n_starts, kmax);
 }
 
 // the 16 bases starting at offset o (0..31) of the group, first base in bits 31:30
@@ -119,18 +178,15 @@ __device__ __forceinline__ bool uniform_group(const Group &g, int kmax)
 }
 
 // direct path for a group that touches a break or the end of the owned range (same as k_count's slow path)
-__device__ __forceinline__ void slow_group(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk,
-                                           uint64_t g, uint64_t n_starts, int kmin, int kmax,
+__device__ __forceinline__ void slow_group(const Group &G, uint64_t g, uint64_t n_starts, int kmin, int kmax,
                                            uint32_t *__restrict__ tables, const TableOffs &offs)
 {
     const uint64_t p0 = g * 32;
     if (p0 >= n_starts) return;
-    const uint32_t w0 = packed[2 * g], w1 = packed[2 * g + 1], w2 = packed[2 * g + 2];
-    const uint32_t b0 = brk[g], b1 = brk[g + 1];
     const int lim = (int)min((uint64_t)32, n_starts - p0);
     for (int o = 0; o < lim; ++o) {
-        const uint32_t W = o < 16 ? __funnelshift_l(w1, w0, 2 * o) : __funnelshift_l(w2, w1, 2 * (o - 16));
-        const uint32_t B = __funnelshift_l(b1, b0, o);
+        const uint32_t W = o < 16 ? __funnelshift_l(G.w1, G.w0, 2 * o) : __funnelshift_l(G.w2, G.w1, 2 * (o - 16));
+        const uint32_t B = __funnelshift_l(G.b1, G.b0, o);
         const int v = min(kmax, __clz(B) + 1);
         if (v >= kmin) atomicAdd(tables + offs.off[v] + (W >> (32 - 2 * v)), 1u);
     }
@@ -146,9 +202,10 @@ __device__ __forceinline__ void add_element(uint32_t *__restrict__ top, uint32_t
 // ---- (1) per-prefix counts of the fast groups of a strided sample ------------------------------------
 // Sampled group i is group (i / 32) * 32 * stride + (i % 32): one warp-tile of 1024 consecutive starts
 // out of every `stride`.
+template <int SRC>
 __global__ void __launch_bounds__(HIST_THREADS)
-k_bucket_hist(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmax,
-              int pb, uint64_t n_sampled, uint32_t stride, uint32_t *__restrict__ bucket_cnt)
+k_bucket_hist(GenomeSrc S, uint64_t n_starts, int kmax, int pb, uint64_t n_sampled, uint32_t stride,
+              uint32_t *__restrict__ bucket_cnt)
 {
     extern __shared__ uint32_t h[];
     const uint32_t nb = 1u << pb;
@@ -157,7 +214,7 @@ k_bucket_hist(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ 
     const int sh = 32 - pb;
     for (uint64_t i = blockIdx.x * (uint64_t)HIST_THREADS + threadIdx.x; i < n_sampled; i += (uint64_t)gridDim.x * HIST_THREADS) {
         const uint64_t g = (i >> 5) * 32 * stride + (i & 31);
-        const Group G = load_group(packed, brk, g, n_starts, kmax);
+        const Group G = load_group<SRC>(S, g, n_starts, kmax);
         if (G.fast && !uniform_group(G, kmax)) {               // uniform groups never reach the buckets
 #pragma unroll
             for (int o = 0; o < 32; o += 2) atomicAdd(&h[window(G, o) >> sh], 1u);
@@ -293,9 +350,9 @@ __device__ __forceinline__ uint4 pad_partial_chunk(uint4 v, uint32_t nv, uint32_
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-template <int KMAX>
+template <int KMAX, int SRC>
 __global__ void __launch_bounds__(PT_THREADS, 1)
-k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ brk, uint64_t n_starts, int kmin,
+k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
             uint32_t *__restrict__ tables, TableOffs offs, const uint32_t *__restrict__ base,
             const uint32_t *__restrict__ init_g, uint32_t *__restrict__ cursor, uint16_t *__restrict__ data,
             uint32_t n_tiles, unsigned long long *__restrict__ stats)
@@ -347,15 +404,15 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
     // flight while the current one is scattered (past the last group: past n_starts, nothing is loaded)
     const uint64_t n_groups_all = (uint64_t)n_tiles * (PT_THREADS * PT_GP);
     uint64_t g = (uint64_t)blockIdx.x * (PT_THREADS * PT_GP) + tid;
-    RawGroup R = prefetch_group(packed, brk, g, n_starts);
+    RawGroup<SRC> R = prefetch_group<SRC>(S, g, n_starts);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int gp = 0; gp < PT_GP; ++gp) {
-            const Group G = finish_group(R, g, n_starts, KMAX);
+            const Group G = finish_group<SRC>(R, g, n_starts, KMAX);
             const uint64_t g_cur = g;
             g = gp + 1 < PT_GP ? g + PT_THREADS
                                : (uint64_t)(tile + gridDim.x) * (PT_THREADS * PT_GP) + tid;
-            R = prefetch_group(packed, brk, g, g < n_groups_all ? n_starts : 0);
+            R = prefetch_group<SRC>(S, g, g < n_groups_all ? n_starts : 0);
             // ---- every element takes its staging slot ----
             if (G.fast) {
                 if (uniform_group(G, KMAX)) {                  // poly-A, (AC)n, mode B's N -> G: 16 equal elements
@@ -411,7 +468,7 @@ k_partition(const uint32_t *__restrict__ packed, const uint32_t *__restrict__ br
                     }
                 }
             } else {
-                slow_group(packed, brk, g_cur, n_starts, kmin, KMAX, tables, offs);
+                slow_group(G, g_cur, n_starts, kmin, KMAX, tables, offs);
                 if (g_cur * 32 < n_starts) atomicAdd(&s_stats[3], 1u);
             }
         }
@@ -618,7 +675,7 @@ int swga_count_partition_supported(uint64_t n_starts, int kmax, int *ok)
 
 // Partitioned accumulate.  Returns SWGA_OK and sets *done = 1 when it handled the request, *done = 0
 // when the shape is outside its range (the caller then uses the direct kernel).
-int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, const uint32_t *d_brk, uint64_t n_starts,
+int swga_count_accumulate_partitioned(swga_ctx *ctx, const GenomeSrc &src, int src_kind, uint64_t n_starts,
                                       int kmin, int kmax, uint32_t *d_tables, cudaStream_t stream, int *done)
 {
     *done = 0;
@@ -660,21 +717,31 @@ int swga_count_accumulate_partitioned(swga_ctx *ctx, const uint32_t *d_packed, c
         CUDA_TRY(cudaEventRecord(ctx->ev_stage[0], stream));
     }
     const int grid_h = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (n_sampled + HIST_THREADS - 1) / HIST_THREADS);
-    SWGA_NOTE_LAUNCH(); k_bucket_hist<<<grid_h, HIST_THREADS, nb * 4, stream>>>(d_packed, d_brk, n_starts, kmax, pb, n_sampled, stride, sample);
+    SWGA_NOTE_LAUNCH();
+    if (src_kind == SRC_PACKED) k_bucket_hist<SRC_PACKED><<<grid_h, HIST_THREADS, nb * 4, stream>>>(src, n_starts, kmax, pb, n_sampled, stride, sample);
+    else if (src_kind == SRC_ASCII) k_bucket_hist<SRC_ASCII><<<grid_h, HIST_THREADS, nb * 4, stream>>>(src, n_starts, kmax, pb, n_sampled, stride, sample);
+    else k_bucket_hist<SRC_ASCII_N><<<grid_h, HIST_THREADS, nb * 4, stream>>>(src, n_starts, kmax, pb, n_sampled, stride, sample);
     SWGA_NOTE_LAUNCH(); k_bucket_layout<<<1, 1024, 0, stream>>>(sample, nb, n_groups, n_sampled, ratio, pad, capacity, base, cursor, init);
     if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[1], stream));
     const size_t smem_p = (size_t)nb * 4 * 2 + PT_OVF_CAP * 4 + PT_AGG * 8 + PT_STAGE * 2;
     const uint32_t grid_p = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count);
-#define LAUNCH_PARTITION(K)                                                                                              \
+#define LAUNCH_PARTITION(K, SRC)                                                                                         \
     do {                                                                                                                 \
-        CUDA_TRY(cudaFuncSetAttribute(k_partition<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));        \
+        CUDA_TRY(cudaFuncSetAttribute(k_partition<K, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));   \
         SWGA_NOTE_LAUNCH();                                                                                              \
-        k_partition<K><<<grid_p, PT_THREADS, smem_p, stream>>>(d_packed, d_brk, n_starts, kmin, d_tables, offs, base,    \
-                                                               init, cursor, data, n_tiles, stats);                      \
+        k_partition<K, SRC><<<grid_p, PT_THREADS, smem_p, stream>>>(src, n_starts, kmin, d_tables, offs, base, init,     \
+                                                                    cursor, data, n_tiles, stats);                       \
     } while (0)
-    if (kmax == 12) LAUNCH_PARTITION(12);
-    else if (kmax == 11) LAUNCH_PARTITION(11);
-    else LAUNCH_PARTITION(10);
+#define LAUNCH_PARTITION_K(K)                                                                                            \
+    do {                                                                                                                 \
+        if (src_kind == SRC_PACKED) LAUNCH_PARTITION(K, SRC_PACKED);                                                     \
+        else if (src_kind == SRC_ASCII) LAUNCH_PARTITION(K, SRC_ASCII);                                                  \
+        else LAUNCH_PARTITION(K, SRC_ASCII_N);                                                                           \
+    } while (0)
+    if (kmax == 12) LAUNCH_PARTITION_K(12);
+    else if (kmax == 11) LAUNCH_PARTITION_K(11);
+    else LAUNCH_PARTITION_K(10);
+#undef LAUNCH_PARTITION_K
 #undef LAUNCH_PARTITION
     if (timing) CUDA_TRY(cudaEventRecord(ctx->ev_stage[2], stream));
     SWGA_NOTE_LAUNCH(); k_item_prefix<<<1, 1024, 0, stream>>>(base, cursor, nb, item_prefix);

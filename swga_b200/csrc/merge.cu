@@ -14,6 +14,7 @@
 //     the four-way sums in shared memory; these are the marginal part of the level below, to which it adds the
 //     ranks' tail counts of that level (same load / sum / store), and so on down to kmin.
 //
+// With world = 1 the same kernel is the single-GPU finalize: one pass over the block instead of one launch per level.
 // Afterwards every block holds the FINALIZED forward tables of the whole genome: reduce-scatter, finalize of
 // the owned slice and all-gather in one pass; each rank sums and marginalises 1 / world of the tables.
 // The caller brackets the kernel with two device-side barriers across the ranks (swga_b200/dist.py).
@@ -94,7 +95,8 @@ extern "C" int swga_merge_supported(int kmin, int kmax, int world, int *ok)
     ARG_CHECK(ok);
     const int depth = kmax - kmin;
     // a rank's slice of T_kmax must be whole spans of 4^depth codes
-    *ok = kmin >= 2 && kmax <= SWGA_KMAX_LIMIT && depth >= 0 && depth <= MG_MAX_DEPTH && (world == 2 || world == 4 || world == 8) &&
+    *ok = kmin >= 2 && kmax <= SWGA_KMAX_LIMIT && depth >= 0 && depth <= MG_MAX_DEPTH &&
+          (world == 1 || world == 2 || world == 4 || world == 8) &&
           ((1ull << (2 * kmax)) / (unsigned)world) % (1ull << (2 * depth)) == 0;
     return SWGA_OK;
 }
@@ -118,7 +120,8 @@ extern "C" int swga_merge_finalize(swga_ctx *ctx, const uint64_t *h_blocks, int 
     const unsigned grid = (unsigned)(slice / span);
     cudaStream_t st = as_stream(stream);
     SWGA_NOTE_LAUNCH();
-    if (world == 2) k_merge_finalize<2><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
+    if (world == 1) k_merge_finalize<1><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
+    else if (world == 2) k_merge_finalize<2><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
     else if (world == 4) k_merge_finalize<4><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
     else k_merge_finalize<8><<<grid, MG_THREADS, 0, st>>>(pb, offs, kmax, depth, slice * rank, span);
     CUDA_TRY(cudaGetLastError());

@@ -180,16 +180,22 @@ def test_partitioned_kernel_equals_direct_and_oracle(kmin, kmax, oracle, torch_c
     d = torch.from_numpy(seq).cuda()
     out = {}
     try:
-        for impl in (1, 2):
-            _lib.check(lib.swga_ctx_set_count_impl(ctx.h, impl))
-            _, canon = kmers.count_all_device(d, rs, mode_b=False, kmin=kmin, kmax=kmax)
-            torch.cuda.synchronize()
-            out[impl] = u32(canon)
+        # 1 = direct kernel on k_pack's output; 2 = partitioned kernels reading the ASCII bases themselves;
+        # 3 = partitioned kernels on k_pack's output (round-1 data flow, kept for A/B timing)
+        for impl in (1, 2, 3):
+            _lib.check(lib.swga_ctx_set_count_impl(ctx.h, min(impl, 2)))
+            _lib.check(lib.swga_ctx_set_count_via_pack(ctx.h, int(impl == 3)))
+            for mode_b in (False, True):
+                _, canon = kmers.count_all_device(d, rs, mode_b=mode_b, kmin=kmin, kmax=kmax)
+                torch.cuda.synchronize()
+                out[impl, mode_b] = u32(canon)
     finally:
         _lib.check(lib.swga_ctx_set_count_impl(ctx.h, 0))
-    assert np.array_equal(out[1], out[2])
-    want = oracle.count_dense_allk(seq, rs, kmin, kmax, mode_b=0)
-    assert np.array_equal(out[2], want)
+        _lib.check(lib.swga_ctx_set_count_via_pack(ctx.h, 0))
+    for mode_b in (False, True):
+        assert np.array_equal(out[1, mode_b], out[2, mode_b]) and np.array_equal(out[3, mode_b], out[2, mode_b])
+        want = oracle.count_dense_allk(seq, rs, kmin, kmax, mode_b=int(mode_b))
+        assert np.array_equal(out[2, mode_b], want)
 
 
 @pytest.mark.parametrize("mode_b", [False, True])
@@ -513,7 +519,16 @@ def test_merge_finalize_kernel_emulated_ranks(world, kmin, kmax, torch_cuda):
     want = blocks[0].clone()
     for b in blocks[1:]:
         want += b
-    _lib.check(lib.swga_count_finalize(ctx.h, kmin, kmax, _lib.ptr(want), None))
+    # the prefix marginalisation T_k[x] += sum_b T_{k+1}[4x + b] (include/swga_b200.h), written out with torch ops
+    offs = [int(lib.swga_table_offset(kmin, k)) for k in range(kmin, kmax + 2)]
+    for k in range(kmax - 1, kmin - 1, -1):
+        lo, up = offs[k - kmin], offs[k + 1 - kmin]
+        want[lo:up] += want[up:offs[k + 2 - kmin]].view(-1, 4).sum(1).to(torch.int32)
+    single = blocks[0].clone()                                     # world = 1: swga_count_finalize itself
+    for b in blocks[1:]:
+        single += b
+    _lib.check(lib.swga_count_finalize(ctx.h, kmin, kmax, _lib.ptr(single), None))
+    assert torch.equal(single, want)
     ptrs = np.array([b.data_ptr() for b in blocks], dtype=np.uint64)
     for rank in range(world):
         _lib.check(lib.swga_merge_finalize(ctx.h, _lib.ptr(ptrs), world, rank, kmin, kmax, None))
