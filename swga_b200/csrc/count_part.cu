@@ -36,6 +36,7 @@
 #define PT_THREADS 1024                             // one CTA per SM
 #define PT_EPG 16                                   // elements per group of 32 starts (the even offsets)
 #define PT_GP 2                                     // groups per thread and tile
+#define PT_BATCH 4                                  // elements whose slot atomics are issued together
 #define PT_TILE_STARTS (PT_THREADS * 32 * PT_GP)    // 65536 starts per tile
 #define PT_TILE_ELEMS (PT_THREADS * PT_EPG * PT_GP) // 32768 elements per tile
 #define PT_LB 15                                    // low bits kept per element (uint16), 32768-bin tables
@@ -72,7 +73,7 @@ template <> struct RawGroup<SRC_PACKED> {
     uint32_t w0, w1, w2, b0, b1;
 };
 struct RawAscii {
-    uint4 a, b, c;                 // bases 0..15, 16..31, 32..47
+    uint4 a, b;                    // bases 0..15, 16..31; the 16 after them come from the next lane when the group is finished
     uint32_t b0, b1;
 };
 template <> struct RawGroup<SRC_ASCII> : RawAscii {};
@@ -118,17 +119,16 @@ __device__ __forceinline__ RawGroup<SRC> prefetch_group(const GenomeSrc &S, uint
         asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.w0), "=r"(r.w1) : "l"(S.packed + 2 * g));
         r.w2 = ldg_nc_u32(S.packed + 2 * g + 2);
     } else {
-        r.a = r.b = r.c = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        if (g * 32 >= n_starts) return r;
+        // loaded whenever the buffer has the bases (not only for owned starts): the lane before needs them as look-ahead
+        r.a = r.b = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         const uint64_t p = g * 32;
-        if (p + 48 <= S.n) {
+        if (p >= S.n || n_starts == 0) return r;
+        if (p + 32 <= S.n) {
             r.a = ldg_nc_v4(S.ascii + p);
             r.b = ldg_nc_v4(S.ascii + p + 16);
-            r.c = ldg_nc_v4(S.ascii + p + 32);
-        } else {                                               // the last groups of the buffer
+        } else {                                               // the last group of the buffer
             r.a = ascii16_edge(S.ascii, p, S.n);
             r.b = ascii16_edge(S.ascii, p + 16, S.n);
-            r.c = ascii16_edge(S.ascii, p + 32, S.n);
         }
     }
     r.b0 = ldg_nc_u32(S.brk + g);
@@ -136,19 +136,33 @@ __device__ __forceinline__ RawGroup<SRC> prefetch_group(const GenomeSrc &S, uint
     return r;
 }
 
+// Must be called by all 32 lanes of a warp, lane l holding group g0 + l (SRC_ASCII*: the 16 bases after a group are
+// the first 16 of the next lane's; lane 31 reads them itself -- the next warp has them in L1 already).
 template <int SRC>
-__device__ __forceinline__ Group finish_group(const RawGroup<SRC> &r, uint64_t g, uint64_t n_starts, int kmax)
+__device__ __forceinline__ Group finish_group(const GenomeSrc &S, const RawGroup<SRC> &r, uint64_t g, uint64_t n_starts, int kmax)
 {
     Group G;
     G.b0 = r.b0; G.b1 = r.b1;
     if constexpr (SRC == SRC_PACKED) {
         G.w0 = r.w0; G.w1 = r.w1; G.w2 = r.w2;
     } else {
-        G.w0 = pack16(r.a); G.w1 = pack16(r.b); G.w2 = pack16(r.c);
+        G.w0 = pack16(r.a); G.w1 = pack16(r.b);
+        uint32_t fa = 0;
+        if constexpr (SRC == SRC_ASCII_N) fa = flags16(r.a, SWGA_MASK_N);
+        uint32_t w2 = __shfl_down_sync(0xffffffffu, G.w0, 1), fc = __shfl_down_sync(0xffffffffu, fa, 1);
+        if ((threadIdx.x & 31) == 31) {
+            const uint64_t p = g * 32 + 32;
+            uint4 c = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            if (n_starts != 0 && p + 16 <= S.n) c = ldg_nc_v4(S.ascii + p);
+            else if (n_starts != 0 && p < S.n) c = ascii16_edge(S.ascii, p, S.n);
+            w2 = pack16(c);
+            if constexpr (SRC == SRC_ASCII_N) fc = flags16(c, SWGA_MASK_N);
+        }
+        G.w2 = w2;
         if constexpr (SRC == SRC_ASCII_N) {
             // an 'N' at base i forbids the windows over (i-1, i) and (i, i+1): brk[j] = bad[j] | bad[j+1]  (k_pack)
-            const uint32_t badA = (flags16(r.a, SWGA_MASK_N) << 16) | flags16(r.b, SWGA_MASK_N);
-            const uint32_t badC = flags16(r.c, SWGA_MASK_N) << 16;
+            const uint32_t badA = (fa << 16) | flags16(r.b, SWGA_MASK_N);
+            const uint32_t badC = fc << 16;
             G.b0 |= badA | (badA << 1) | (badC >> 31);
             G.b1 |= badC | (badC << 1);                        // only its leading kmax-2 bits are looked at
         }
@@ -162,7 +176,7 @@ __device__ __forceinline__ Group finish_group(const RawGroup<SRC> &r, uint64_t g
 template <int SRC>
 __device__ __forceinline__ Group load_group(const GenomeSrc &S, uint64_t g, uint64_t n_starts, int kmax)
 {
-    return finish_group<SRC>(prefetch_group<SRC>(S, g, n_starts), g, n_starts, kmax);
+    return finish_group<SRC>(S, prefetch_group<SRC>(S, g, n_starts), g, n_starts, kmax);
 }
 
 // the 16 bases starting at offset o (0..31) of the group, first base in bits 31:30
@@ -212,10 +226,12 @@ k_bucket_hist(GenomeSrc S, uint64_t n_starts, int kmax, int pb, uint64_t n_sampl
     for (uint32_t i = threadIdx.x; i < nb; i += HIST_THREADS) h[i] = 0;
     __syncthreads();
     const int sh = 32 - pb;
-    for (uint64_t i = blockIdx.x * (uint64_t)HIST_THREADS + threadIdx.x; i < n_sampled; i += (uint64_t)gridDim.x * HIST_THREADS) {
+    // warp-uniform trip count: load_group is a warp-wide call (the lanes hold 32 consecutive groups)
+    for (uint64_t i0 = blockIdx.x * (uint64_t)HIST_THREADS + (threadIdx.x & ~31u); i0 < n_sampled; i0 += (uint64_t)gridDim.x * HIST_THREADS) {
+        const uint64_t i = i0 + (threadIdx.x & 31u);
         const uint64_t g = (i >> 5) * 32 * stride + (i & 31);
         const Group G = load_group<SRC>(S, g, n_starts, kmax);
-        if (G.fast && !uniform_group(G, kmax)) {               // uniform groups never reach the buckets
+        if (i < n_sampled && G.fast && !uniform_group(G, kmax)) {   // uniform groups never reach the buckets
 #pragma unroll
             for (int o = 0; o < 32; o += 2) atomicAdd(&h[window(G, o) >> sh], 1u);
         }
@@ -408,7 +424,7 @@ k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int gp = 0; gp < PT_GP; ++gp) {
-            const Group G = finish_group<SRC>(R, g, n_starts, KMAX);
+            const Group G = finish_group<SRC>(S, R, g, n_starts, KMAX);
             const uint64_t g_cur = g;
             g = gp + 1 < PT_GP ? g + PT_THREADS
                                : (uint64_t)(tile + gridDim.x) * (PT_THREADS * PT_GP) + tid;
@@ -422,21 +438,31 @@ k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
                 } else {
                     uint32_t full = 0;                         // bit 15-e: element e (offset 2e) found its range full
                     uint32_t prev = 0xffffffffu;
+                    // batches of PT_BATCH elements: their slot atomics are in flight together, then their stores (an atomic
+                    // may not pass an earlier shared store in program order, so one at a time exposes its whole latency)
 #pragma unroll
-                    for (int o = 0; o < 32; o += 2) {
-                        const uint32_t W = window(G, o);
-                        const uint32_t boff = (W >> (30 - PB)) & ((NB - 1u) << 2);
-                        // An element that follows one of the same bucket takes the overflow path: a group then adds at
-                        // most 8 to any counter, a tile at most 2^14, and the 14-bit guard cannot wrap (it would
-                        // re-open a full range after 2^14 + range further elements of one tile).
-                        uint32_t old = 0x80000000u;
-                        if (boff != prev)
-                            old = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
-                        prev = boff;
-                        // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on
-                        // a 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
-                        if ((int32_t)old >= 0) stg[(old & 0x1FFFFu) ^ ((boff >> 2) & 7u)] = (uint16_t)((W >> SHE) & LMASK);
-                        full = __funnelshift_l(old, full, 1);
+                    for (int o0 = 0; o0 < 32; o0 += 2 * PT_BATCH) {
+                        uint32_t W[PT_BATCH], sw[PT_BATCH], old[PT_BATCH];
+#pragma unroll
+                        for (int j = 0; j < PT_BATCH; ++j) {
+                            W[j] = window(G, o0 + 2 * j);
+                            const uint32_t boff = (W[j] >> (30 - PB)) & ((NB - 1u) << 2);
+                            // An element that follows one of the same bucket takes the overflow path: a group then adds
+                            // at most 8 to any counter, a tile at most 2^14, and the 14-bit guard cannot wrap (it would
+                            // re-open a full range after 2^14 + range further elements of one tile).
+                            old[j] = 0x80000000u;
+                            if (boff != prev)
+                                old[j] = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
+                            prev = boff;
+                            sw[j] = (boff >> 2) & 7u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < PT_BATCH; ++j) {
+                            // slot inside its 8-element chunk is xor-ed with the bucket's low bits: all ranges start on a
+                            // 16-byte boundary and fill in step, which would put every early store on 8 of the 32 banks
+                            if ((int32_t)old[j] >= 0) stg[(old[j] & 0x1FFFFu) ^ sw[j]] = (uint16_t)((W[j] >> SHE) & LMASK);
+                            full = __funnelshift_l(old[j], full, 1);
+                        }
                     }
                     while (full) {                             // rare: the tile's composition is off the sample's
                         const int e = __clz(full) - 16;
@@ -529,36 +555,46 @@ k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
                 }
             }
         }
-        // pass B: copy the whole chunks, move the left-over chunk to the head of the range
+        // pass B: copy the whole chunks -- a PAIR of lanes per bucket, so that the two chunks a bucket typically sends
+        // per tile are adjacent 16-byte stores of one instruction (one L1 wavefront instead of two: the profile showed
+        // the write-out bound by the wavefronts of uncoalesced stores) -- then move the left-over chunk to the head
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t unit = r * WARPS + warp;
             if (unit >= UNITS) continue;
-            const uint32_t b = unit * 32 + lane;
-            const uint32_t u = u_[r], at = at_[r], lim = lim_[r];
-            const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;
-            const uint4 *sp = reinterpret_cast<const uint4 *>(stg + s0_[r]);
-            for (uint32_t cc = 0; cc < ru; cc += 8u, ++sp) {
-                uint4 v = *sp;
-                if (u - cc < 8u) v = pad_partial_chunk(v, u - cc, b & 7u, padv);   // last tile only
-                if (at + cc + 8u <= lim) {
-                    *reinterpret_cast<uint4 *>(data + at + cc) = v;
-                } else {                                       // the run crosses the end of its bucket: straight to the table
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-                        if (e <= LMASK) {
-                            add_element(top, (b << PT_LB) | e, KMAX);
-                            atomicAdd(&s_stats[1], 1u);
+            for (int h = 0; h < 2; ++h) {
+                const int src = 16 * h + (int)(lane >> 1);
+                const uint32_t b = unit * 32 + src;
+                const uint32_t u = __shfl_sync(0xffffffffu, u_[r], src), s0 = __shfl_sync(0xffffffffu, s0_[r], src);
+                const uint32_t at = __shfl_sync(0xffffffffu, at_[r], src), lim = __shfl_sync(0xffffffffu, lim_[r], src);
+                const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;
+                for (uint32_t cc = (lane & 1u) * 8u; cc < ru; cc += 16u) {
+                    uint4 v = *reinterpret_cast<const uint4 *>(stg + s0 + cc);
+                    if (u - cc < 8u) v = pad_partial_chunk(v, u - cc, b & 7u, padv);   // last tile only
+                    if (at + cc + 8u <= lim) {
+                        *reinterpret_cast<uint4 *>(data + at + cc) = v;
+                    } else {                                   // the run crosses the end of its bucket: straight to the table
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t e = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                            if (e <= LMASK) {
+                                add_element(top, (b << PT_LB) | e, KMAX);
+                                atomicAdd(&s_stats[1], 1u);
+                            }
                         }
                     }
                 }
             }
-            // the left-over chunk moves to the head of the range (it is read before it is overwritten: same lane)
-            if (!last && (u & 7u) && ru) {
-                uint4 *hp = reinterpret_cast<uint4 *>(stg + s0_[r]);
-                *hp = hp[ru >> 3];
+            __syncwarp();                                      // the head chunk may still be read by the pair's other lane
+            {
+                const uint32_t u = u_[r];
+                const uint32_t ru = last ? (u + 7u) & ~7u : u & ~7u;
+                if (!last && (u & 7u) && ru) {
+                    uint4 *hp = reinterpret_cast<uint4 *>(stg + s0_[r]);
+                    *hp = hp[ru >> 3];
+                }
             }
         }
         __syncthreads();
