@@ -206,6 +206,14 @@ __device__ __forceinline__ void slow_group(const Group &G, uint64_t g, uint64_t 
     }
 }
 
+// atom.shared.add.u32 on a 32-bit shared-memory address
+__device__ __forceinline__ uint32_t atomicAdd_shared(uint32_t addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+
 // both kmax-mers of an element (code = 2 (kmax+1) bits), straight to the top table
 __device__ __forceinline__ void add_element(uint32_t *__restrict__ top, uint32_t code, int kmax)
 {
@@ -390,6 +398,9 @@ k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
     __shared__ uint32_t s_stats[4];                            // exits taken: staging full, bucket full, uniform, slow groups
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *__restrict__ top = tables + offs.off[KMAX];
+    __shared__ uint32_t s_dummy[32];                           // target of the atomics of skipped elements, one word per lane
+    const uint32_t fill_s = (uint32_t)__cvta_generic_to_shared(fill);
+    const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + lane);
     if (tid < 4) s_stats[tid] = 0;
 
     // Padding (only the last chunk a CTA writes into a bucket, and the chunks of the overflow list, carry any):
@@ -450,9 +461,11 @@ k_partition(GenomeSrc S, uint64_t n_starts, int kmin,
                             // An element that follows one of the same bucket takes the overflow path: a group then adds
                             // at most 8 to any counter, a tile at most 2^14, and the 14-bit guard cannot wrap (it would
                             // re-open a full range after 2^14 + range further elements of one tile).
-                            old[j] = 0x80000000u;
-                            if (boff != prev)
-                                old[j] = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(fill) + boff), PT_ADD);
+                            // (branch-free: the skipped atomic goes to a per-lane dummy word instead; a conditional atomic
+                            // compiles to a branch with a reconvergence barrier, five more instructions per element)
+                            const bool dup = boff == prev;
+                            const uint32_t got = atomicAdd_shared(dup ? dummy_s : fill_s + boff, PT_ADD);
+                            old[j] = dup ? 0x80000000u : got;
                             prev = boff;
                             sw[j] = (boff >> 2) & 7u;
                         }
