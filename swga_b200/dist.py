@@ -158,12 +158,22 @@ class PeerTableMerge(TableMerge):
 
 
 def table_merge(words, kmin, kmax, device, prefer="peer"):
-    """The best merge this job supports: the fused peer-memory kernel, else the NCCL all_reduce."""
+    """The best merge this job supports: the fused peer-memory kernel, else the NCCL all_reduce.  The choice is made
+    TOGETHER: a rank whose symmetric-memory set-up fails must not leave the others waiting in a barrier, so every rank
+    reports its outcome and all fall back if any did."""
+    import torch
+    import torch.distributed as td
     if prefer == "peer":
+        m, err = None, ""
         try:
-            return PeerTableMerge(words, kmin, kmax, device)
+            m = PeerTableMerge(words, kmin, kmax, device)
         except Exception as e:                                  # no symmetric memory / no P2P on this box
-            m = TableMerge(words, kmin, kmax, device)
-            m.name += " (peer merge unavailable: %s)" % (repr(e)[:200],)
+            err = repr(e)[:200]
+        ok = torch.tensor([1 if m is not None else 0], dtype=torch.int32, device=device)
+        td.all_reduce(ok, op=td.ReduceOp.MIN)
+        if int(ok.item()) == 1:
             return m
+        m = TableMerge(words, kmin, kmax, device)
+        m.name += " (peer merge unavailable%s)" % (": " + err if err else " on another rank")
+        return m
     return TableMerge(words, kmin, kmax, device)
