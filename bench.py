@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-bases", type=int, default=None,
                     help="bases of the background prefix the CPU arm counts per step (default: 10 Mbp in the "
                          "reference arm, 5 Mbp in the cpu_baseline leg of the b200 arm)")
-    ap.add_argument("--cpu-budget-s", type=float, default=1200.0,
+    ap.add_argument("--cpu-budget-s", type=float, default=900.0,
                     help="reference arm: shrink the sample so that all timed steps fit this many seconds")
     ap.add_argument("--score-sets", type=float, default=1e7, help="candidate sets of the 'typical' scoring workload")
     ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
