@@ -3,8 +3,9 @@
 Counting shards the linearised genome into contiguous chunks of START positions; each rank also
 receives the kmax-1 bases after its last start (right halo), so a k-mer is owned by the rank that
 owns its first base.  Record boundaries inside the chunk (and its halo) travel as chunk-local record
-starts.  Per-rank tables are in the additive "top-k + tails" form (include/swga_b200.h), merged by
-ONE allreduce(sum) over NCCL/NVLink, then finalised identically on every rank.
+starts.  Per-rank tables are in the additive "top-k + tails" form (include/swga_b200.h), merged by ONE kernel per
+rank over NVLink peer memory that also finalises them (PeerTableMerge, csrc/merge.cu) -- or, where symmetric memory
+is not available, by one NCCL allreduce(sum) followed by the finalize pass on every rank (TableMerge).
 
 Set scoring shards by set index with no collective (see swga_b200/score.py).
 """
