@@ -8,6 +8,8 @@ import torch
 from swga_b200 import _lib, kmers, synth
 
 lib, ctx = _lib.load(), _lib.context(0)
+if os.environ.get("SWGA_VIA_PACK"):
+    _lib.check(lib.swga_ctx_set_count_via_pack(ctx.h, 1))
 seed, n, gc, n_rec = synth.CONFIGS["C2_bg"]
 if len(sys.argv) > 1:
     n = int(float(sys.argv[1]))
