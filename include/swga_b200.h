@@ -157,6 +157,11 @@ int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint32_t *d_fwd
  * kmax - kmin <= 7 (swga_merge_supported).  With all pointers on one device and the ranks run one after another
  * it is also a plain multi-block sum + finalize (tests). */
 int swga_merge_supported(int kmin, int kmax, int world, int *ok);
+/* The same pass through the NVSwitch: d_multicast is the MULTICAST mapping of the ranks' blocks (one address = the
+ * same offset in every block; torch symmetric memory's multicast_ptr).  multimem.ld_reduce sums the ranks' words inside
+ * the switch, multimem.st writes the finalized slice into every block. */
+int swga_merge_finalize_multicast(swga_ctx *ctx, uint32_t *d_multicast, int world, int rank, int kmin, int kmax,
+                                  void *stream);
 int swga_merge_finalize(swga_ctx *ctx, const uint64_t *h_blocks, int world, int rank, int kmin, int kmax,
                         void *stream);
 

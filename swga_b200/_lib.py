@@ -52,6 +52,7 @@ SIGNATURES = {
     "swga_fold_canonical": (ctypes.c_int, [c_ctx, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "swga_merge_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "swga_merge_finalize": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
+    "swga_merge_finalize_multicast": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     "swga_count_genome_device": (ctypes.c_int, [c_ctx, c_vp, ctypes.c_uint64, c_vp, ctypes.c_uint64, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
                                                 c_vp, c_vp, c_vp]),

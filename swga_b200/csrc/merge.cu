@@ -20,7 +20,7 @@
 // The caller brackets the kernel with two device-side barriers across the ranks (swga_b200/dist.py).
 #include "common.cuh"
 
-#define MG_THREADS 256
+#define MG_THREADS 1024                             // remote loads are latency-bound: many 16-byte loads in flight per SM
 #define MG_MAX_WORLD 8
 #define MG_MAX_DEPTH 7                              // levels below kmax finished inside one CTA: span = 4^7 codes of T_kmax
 
@@ -90,6 +90,87 @@ k_merge_finalize(PeerBlocks blocks, TableOffs offs, int kmax, int depth, uint64_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same pass through the NVSwitch: `mc` is the MULTICAST mapping of the ranks' blocks (one address = the same
+// offset in every block).  multimem.ld_reduce returns the sum over all ranks, added up INSIDE the switch (each GPU
+// sends its words once, the owner receives one reduced word instead of one per rank), multimem.st writes the result
+// into every block.  Pairs of 32-bit counts travel as one 64-bit integer: exact while every summed count stays below
+// 2^32 (the table's own range; beyond it the peer-pointer kernel wraps each count modulo 2^32 and this one carries
+// into the neighbour -- the reference drops such counts, ext/dsk/minia/Utils.cpp:6).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mc_ld_reduce_u64(const uint32_t *a)
+{
+    unsigned long long v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_u64(uint32_t *a, unsigned long long v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t mc_ld_reduce_u32(const uint32_t *a)
+{
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_u32(uint32_t *a, uint32_t v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+
+// One CTA: span codes of level kmax from c0 on, then the levels below (as k_merge_finalize).  A lane handles one PAIR of
+// adjacent codes per step (8 contiguous bytes: a warp reads 256 contiguous bytes); the four children of a code are two
+// pairs = two adjacent lanes.
+__global__ void __launch_bounds__(MG_THREADS)
+k_merge_finalize_mc(uint32_t *__restrict__ mc, TableOffs offs, int kmax, int depth, uint64_t slice_start, uint32_t span)
+{
+    __shared__ __align__(16) uint32_t bufA[4096], bufB[1024];
+    uint32_t *marg = bufA, *next = bufB;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t c0 = slice_start + (uint64_t)blockIdx.x * span;
+    uint32_t n = span;
+    for (int lv = 0; lv <= depth; ++lv) {
+        const int k = kmax - lv;
+        uint32_t *tab = mc + offs.off[k] + c0;
+        uint32_t *out = lv == 0 ? marg : next;
+        if (n >= 4) {
+            const uint32_t pairs = n / 2;
+            for (uint32_t p0 = threadIdx.x & ~31u; p0 < pairs; p0 += MG_THREADS) {       // warp-uniform trip count
+                const uint32_t p = p0 + lane;
+                const bool on = p < pairs;
+                uint32_t lo = 0, hi = 0;
+                if (on) {
+                    const unsigned long long v = mc_ld_reduce_u64(tab + 2ull * p);
+                    lo = (uint32_t)v;
+                    hi = (uint32_t)(v >> 32);
+                    if (lv > 0) {
+                        const uint2 m = reinterpret_cast<const uint2 *>(marg)[p];
+                        lo += m.x;
+                        hi += m.y;
+                    }
+                    mc_st_u64(tab + 2ull * p, (unsigned long long)lo | ((unsigned long long)hi << 32));
+                }
+                uint32_t s = lo + hi;
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (on && !(p & 1u)) out[p >> 1] = s;
+            }
+        } else if (threadIdx.x == 0) {
+            uint32_t s = lv > 0 ? marg[0] : 0u;
+            s += mc_ld_reduce_u32(tab);
+            mc_st_u32(tab, s);
+        }
+        __syncthreads();
+        if (lv > 0) {
+            uint32_t *t = marg;
+            marg = next;
+            next = t;
+        }
+        c0 >>= 2;
+        n >>= 2;
+    }
+}
+
 extern "C" int swga_merge_supported(int kmin, int kmax, int world, int *ok)
 {
     ARG_CHECK(ok);
@@ -98,6 +179,27 @@ extern "C" int swga_merge_supported(int kmin, int kmax, int world, int *ok)
     *ok = kmin >= 2 && kmax <= SWGA_KMAX_LIMIT && depth >= 0 && depth <= MG_MAX_DEPTH &&
           (world == 1 || world == 2 || world == 4 || world == 8) &&
           ((1ull << (2 * kmax)) / (unsigned)world) % (1ull << (2 * depth)) == 0;
+    return SWGA_OK;
+}
+
+// d_multicast: the multicast mapping of the ranks' blocks (torch symmetric memory: multicast_ptr)
+extern "C" int swga_merge_finalize_multicast(swga_ctx *ctx, uint32_t *d_multicast, int world, int rank, int kmin, int kmax,
+                                             void *stream)
+{
+    ARG_CHECK(ctx && d_multicast && rank >= 0 && rank < world && world >= 2);
+    int ok = 0;
+    TRY(swga_merge_supported(kmin, kmax, world, &ok));
+    if (!ok) {
+        swga_set_error("swga_merge_finalize_multicast: unsupported shape kmin=%d kmax=%d world=%d", kmin, kmax, world);
+        return SWGA_E_ARG;
+    }
+    const TableOffs offs = swga_make_offs(kmin, kmax);
+    const int depth = kmax - kmin;
+    const uint64_t slice = (1ull << (2 * kmax)) / (unsigned)world;
+    const uint32_t span = 1u << (2 * depth);
+    SWGA_NOTE_LAUNCH();
+    k_merge_finalize_mc<<<(unsigned)(slice / span), MG_THREADS, 0, as_stream(stream)>>>(d_multicast, offs, kmax, depth, slice * rank, span);
+    CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }
 

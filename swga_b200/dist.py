@@ -106,7 +106,7 @@ class PeerTableMerge(TableMerge):
 
     name = "k_merge_finalize: fused reduce-scatter + finalize + all-gather over NVLink peer mappings; fold on every rank"
 
-    def __init__(self, words, kmin, kmax, device):
+    def __init__(self, words, kmin, kmax, device, use_multicast=True):
         import ctypes
         import torch
         import torch.distributed as td
@@ -127,8 +127,24 @@ class PeerTableMerge(TableMerge):
         self.hdl = symm.rendezvous(self.t, td.group.WORLD)
         self.ptrs = np.array([int(p) for p in self.hdl.buffer_ptrs], dtype=np.uint64)
         assert len(self.ptrs) == self.world and int(self.ptrs[self.rank]) == self.t.data_ptr()
+        # NVSwitch multicast mapping of the blocks (0 when the fabric has none): the in-switch reduction variant
+        self.multicast = 0
+        if use_multicast:
+            try:
+                self.multicast = int(self.hdl.multicast_ptr or 0)
+            except Exception:
+                self.multicast = 0
+        flag = torch.tensor([1 if self.multicast else 0], dtype=torch.int32, device=device)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)                 # every rank or none
+        if int(flag.item()) == 0:
+            self.multicast = 0
+        if self.multicast:
+            self.name = ("k_merge_finalize_mc: reduce-scatter INSIDE the NVSwitch (multimem.ld_reduce) + finalize + all-gather "
+                         "(multimem.st) in one kernel; fold on every rank")
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
+        self.time_kernel = False                               # bench.py: CUDA events around the kernel, on its stream
+        self.kernel_events = []
 
     def block(self):
         return self.t
@@ -141,8 +157,18 @@ class PeerTableMerge(TableMerge):
         self.side.wait_event(self.ev_in)
         with torch.cuda.stream(self.side):
             self.hdl.barrier(channel=0)                        # every rank has finished accumulating
-            _lib.check(self.lib.swga_merge_finalize(self.ctx.h, _lib.ptr(self.ptrs), self.world, self.rank, self.kmin,
-                                                    self.kmax, self.side.cuda_stream))
+            if self.time_kernel:
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record(self.side)
+            if self.multicast:
+                _lib.check(self.lib.swga_merge_finalize_multicast(self.ctx.h, _lib.ptr(self.multicast), self.world, self.rank,
+                                                                  self.kmin, self.kmax, self.side.cuda_stream))
+            else:
+                _lib.check(self.lib.swga_merge_finalize(self.ctx.h, _lib.ptr(self.ptrs), self.world, self.rank, self.kmin,
+                                                        self.kmax, self.side.cuda_stream))
+            if self.time_kernel:
+                k1.record(self.side)
+                self.kernel_events.append((k0, k1))
             self.hdl.barrier(channel=1)                        # every rank has written its slice everywhere
             self.ev_out.record(self.side)
 
@@ -164,10 +190,10 @@ def table_merge(words, kmin, kmax, device, prefer="peer"):
     reports its outcome and all fall back if any did."""
     import torch
     import torch.distributed as td
-    if prefer == "peer":
+    if prefer in ("peer", "multicast"):
         m, err = None, ""
         try:
-            m = PeerTableMerge(words, kmin, kmax, device)
+            m = PeerTableMerge(words, kmin, kmax, device, use_multicast=(prefer == "multicast"))
         except Exception as e:                                  # no symmetric memory / no P2P on this box
             err = repr(e)[:200]
         ok = torch.tensor([1 if m is not None else 0], dtype=torch.int32, device=device)

@@ -45,22 +45,27 @@ def main():
     # kernel (csrc/merge.cu: reduce-scatter + finalize + all-gather over NVLink mappings), else the NCCL / gloo path ----
     lib = _lib.load()
     words = int(lib.swga_tables_words(5, 12))
-    merge = dist.table_merge(words, 5, 12, torch.device("cuda", dev), prefer="peer" if backend == "nccl" else "nccl")
-    if backend == "nccl":
-        assert isinstance(merge, dist.PeerTableMerge), merge.name
-    for it in range(3):                                            # repeated: the block is re-zeroed and re-merged in place
-        sh = dist.shard_genome(seq, rs, rank, world, kmax=12)
-        d = torch.from_numpy(np.ascontiguousarray(sh.seq)).cuda()
-        fwd = merge.block()
-        fwd.zero_()
-        kmers.count_all_device(d, sh.rec_starts, mode_b=True, n_starts=sh.n_starts, finalize=False, d_fwd=fwd)
-        canon = torch.empty_like(fwd)
-        merge.start(fwd)
-        merge.finish(fwd, canon)
-        torch.cuda.synchronize()
-        want = O.count_dense_allk(seq, rs, 5, 12, mode_b=1)
-        assert np.array_equal(canon.cpu().numpy().view(np.uint32), want), (rank, it, merge.name)
-        td.barrier()
+    names = []
+    for prefer in (("multicast", "peer") if backend == "nccl" else ("nccl",)):
+        merge = dist.table_merge(words, 5, 12, torch.device("cuda", dev), prefer=prefer)
+        names.append(merge.name)
+        if backend == "nccl":
+            assert isinstance(merge, dist.PeerTableMerge), merge.name
+            if prefer == "peer":
+                assert not merge.multicast
+        for it in range(3):                                        # repeated: the block is re-zeroed and re-merged in place
+            sh = dist.shard_genome(seq, rs, rank, world, kmax=12)
+            d = torch.from_numpy(np.ascontiguousarray(sh.seq)).cuda()
+            fwd = merge.block()
+            fwd.zero_()
+            kmers.count_all_device(d, sh.rec_starts, mode_b=True, n_starts=sh.n_starts, finalize=False, d_fwd=fwd)
+            canon = torch.empty_like(fwd)
+            merge.start(fwd)
+            merge.finish(fwd, canon)
+            torch.cuda.synchronize()
+            want = O.count_dense_allk(seq, rs, 5, 12, mode_b=1)
+            assert np.array_equal(canon.cpu().numpy().view(np.uint32), want), (rank, it, merge.name)
+            td.barrier()
     _lib.check(_lib.load().swga_ctx_set_count_impl(_lib.context(dev).h, 0))
     # ---- scoring: every rank scores its contiguous share of the sets; together they equal the unsharded result ----
     g = fasta.Genome(seq[:3_000_000].copy(), np.array([0, 1_200_000, 3_000_000], dtype=np.uint64), ["a", "b"])
@@ -96,7 +101,7 @@ def main():
     td.barrier()
     td.destroy_process_group()
     if rank == 0:
-        print("dist gpu worker ok (%s; merge: %s)" % (backend, merge.name))
+        print("dist gpu worker ok (%s; merges: %s)" % (backend, " | ".join(names)))
 
 
 if __name__ == "__main__":
