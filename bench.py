@@ -52,9 +52,9 @@ def parse_args():
                     help="reference arm: shrink the sample so that all timed steps fit this many seconds")
     ap.add_argument("--score-sets", type=float, default=1e7, help="candidate sets of the 'typical' scoring workload")
     ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
-    ap.add_argument("--merge", default="multicast", choices=["multicast", "peer", "nccl"],
-                    help="cross-GPU merge: the fused kernel with in-switch reduction (multimem; falls back to peer loads when "
-                         "the fabric has no multicast), the fused kernel over peer pointers, or NCCL all_reduce + finalize "
+    ap.add_argument("--merge", default="peer", choices=["peer", "multicast", "nccl"],
+                    help="cross-GPU merge: the fused kernel over peer pointers (default; measured fastest), the same kernel with "
+                         "the reduction inside the NVSwitch (multimem.ld_reduce / multimem.st), or NCCL all_reduce + finalize "
                          "on every rank")
     ap.add_argument("--via-pack", action="store_true", help="A/B: k_pack + partitioned kernels on its output (round-1 data flow)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -427,14 +427,23 @@ def run_b200_arm(args):
     clocks = sampler.summary()
 
     # ---- the merge kernel itself (events on its own stream, between the two barriers) ----
-    merge_kernel_ms = None
+    merge_kernel_ms = merge_alone_ms = None
     if merge is not None and hasattr(merge, "time_kernel"):
         merge.time_kernel = True
         for _ in range(5):
             step()
         barrier()
-        merge.time_kernel = False
         merge_kernel_ms = rank_max([sum(a.elapsed_time(b) for a, b in merge.kernel_events) / max(1, len(merge.kernel_events))])[0]
+        # ... and with nothing else on the GPU (in the step the replicated foreground count shares the SMs with it)
+        merge.kernel_events = []
+        for _ in range(5):
+            bg.accumulate()
+            torch.cuda.synchronize()
+            merge.start(bg.fwd, None)
+            merge.finish(bg.fwd, bg.canon, None)
+        barrier()
+        merge.time_kernel = False
+        merge_alone_ms = rank_max([sum(a.elapsed_time(b) for a, b in merge.kernel_events) / max(1, len(merge.kernel_events))])[0]
 
     # ---- per-kernel times of the count stage: CUDA events recorded inside swga_count_accumulate, on its stream ----
     _lib.check(lib.swga_ctx_set_stage_timing(ctx.h, 1))
@@ -675,7 +684,8 @@ def run_b200_arm(args):
                        if world > 1 else "single GPU", "l2": "inputs (%.2f GB/GPU) larger than L2" % (bg.n / 1e9)},
             "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu, "e2e": e2e,
             "clocks": clocks, "gpu_launches": launches, "numa_node": numa,
-            "merge": {"impl": merge.name, "exposed_ms": merge_ms, "kernel_ms": merge_kernel_ms} if merge is not None else None,
+            "merge": {"impl": merge.name, "exposed_ms": merge_ms, "kernel_ms": merge_kernel_ms,
+                      "kernel_alone_ms": merge_alone_ms} if merge is not None else None,
             "scoring": scoring, "c3": c3, "low_entropy": hostile, "count_merge": count_merge,
             "full_size_properties": props,
         }
