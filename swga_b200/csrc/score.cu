@@ -378,13 +378,158 @@ __device__ __forceinline__ void set_bit_if(uint32_t idx, uint32_t len, uint32_t 
                  ::"r"(idx), "r"(len), "r"(bm_s + 4u * (p >> 5)), "r"(1u << (p & 31)) : "memory");
 }
 
+
+// ---- routed variant of the dense kernel (default) ------------------------------------------------------
+// The bitmap variant spends 60 % of its instructions on divergent bit-extraction loops and the gap pass that follows
+// them (profiles/r01_summary.md).  Here a tile is a per-warp COUNTING SORT instead: lane w owns the window of 256
+// positions [256 w, 256 w + 256) of the tile; every site takes the next slot of its window's 32-byte row with one
+// shared atomicAdd (its value, tile-relative | 0x8000, goes there as uint16); the owner reads its row with 16-byte
+// loads, clears it, sorts the values in registers (Batcher's network: 19 compare-exchanges for 8 values, 63 for 16;
+// empty slots are 0 and sort to the front) and takes the gaps from neighbouring registers -- straight-line predicated
+// code, no loop whose trip count differs between lanes.  The predecessor of a window's first site is the running
+// maximum of the windows before it (one warp scan).  The warp takes the 8-value form when no window of the tile
+// received more than 8 sites (89 % of the C4-dense tiles), the 16-value form up to 16, and dense_tile_slow() --
+// bitmap + per-lane bit walk, in the same shared memory as the rows -- beyond that or when the tile has no predecessor
+// (the first non-empty tile of a warp's range).
+#define DT_ROW_CAP 16u
+
+// Slot of a chunk entry in its window's row.  Branch-free: the atomic of an entry that is not a site of the segment goes to
+// a per-lane dummy counter that starts at 2^30 (a predicated atomic compiles to a branch with a reconvergence barrier
+// around it), so its "slot" is never below DT_ROW_CAP and its store is predicated off like that of a 17th site.
+__device__ __forceinline__ uint32_t route_take(uint32_t addr)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+    return old;
+}
+__device__ __forceinline__ void route_put(uint32_t old, uint32_t row_addr, uint32_t x)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 16;\n\t@p st.shared.u16 [%1], %2;\n\t}"
+                 ::"r"(old), "r"(row_addr + 2u * old), "h"((unsigned short)x) : "memory");
+}
+// Statistics of one gap in the routed kernel.  The histogram has one more bin behind the last (gaps >= hist_bins) and 32
+// dummy words behind that, one per lane, which take the increments of the empty register slots: the update is one
+// unconditional shared-memory increment.  The NUMBER of gaps is not counted here: it is the sum of the bins.
+__device__ __forceinline__ void add_gap_r(GapAcc &acc, uint32_t g, uint32_t bin, uint32_t hist_s)
+{
+    acc.sumsq += (unsigned long long)g * g;
+    acc.maxgap = max(acc.maxgap, g);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * bin) : "memory");
+}
+// The owner's half of a routed tile: v[] = the N values of my window's row (0 = empty slot).  Sorts them, then takes the
+// gap of every site to its predecessor: the register before it, or -- for the first site of the window -- the last
+// site before the window (running maximum over the lanes, `carry` from the tiles before; carry != 0 here).
+template <int N>
+__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base, uint32_t lane, uint32_t &carry, GapAcc &acc,
+                                           uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+{
+    // Batcher's odd-even merge sort, fully unrolled (every index is a compile-time constant)
+#pragma unroll
+    for (int p = 1; p < N; p <<= 1) {
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1) {
+#pragma unroll
+            for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
+#pragma unroll
+                for (int i = 0; i <= (k - 1 < N - j - k - 1 ? k - 1 : N - j - k - 1); ++i) {
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const uint32_t lo_ = min(v[i + j], v[i + j + k]), hi_ = max(v[i + j], v[i + j + k]);
+                        v[i + j] = lo_;
+                        v[i + j + k] = hi_;
+                    }
+                }
+            }
+        }
+    }
+    const uint32_t K = tile_base - 0x8000u + 1u;               // stored value + K = position + 1
+    uint32_t run = v[N - 1] ? v[N - 1] + K : 0u;               // (last position of my window) + 1
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d));
+    uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
+    if (lane == 0) pred = 0;
+    pred = max(pred, carry);                                   // >= 1: this tile has a predecessor
+    const uint32_t predrel = pred - K;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        // empty slot: g = 0 into my dummy word; a site two lists share: g = 0 into bin 0 (never read)
+        const uint32_t pv = (i && v[i ? i - 1 : 0]) ? v[i ? i - 1 : 0] : predrel;
+        const uint32_t g = v[i] ? v[i] - pv : 0u;
+        add_gap_r(acc, g, v[i] ? min(g, bins) : dummy_bin, hist_s);
+    }
+    carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
+}
+
+// One tile through the bitmap, every lane walking its own 8 words (any number of sites, with or without a predecessor).
+// State in and out by value: a variable whose address is passed to a call lives in local memory for the whole kernel.
+struct TileState {
+    uint32_t carry, first, cnt, maxgap;
+    unsigned long long sumsq;
+};
+__device__ __noinline__ TileState dense_tile_slow(const uint32_t *__restrict__ sites, const uint32_t *__restrict__ toff, uint32_t n_tiles,
+                                                  uint32_t hist_bins, const uint32_t *s_list, uint32_t nl, uint32_t t, uint32_t *bm,
+                                                  uint32_t hist_s, TileState st)
+{
+    const uint32_t lane = threadIdx.x & 31u, tile_base = t << DT_SHIFT;
+    for (uint32_t l = 0; l < nl; ++l) {
+        const uint32_t *r = toff + (uint64_t)s_list[l] * (n_tiles + 1) + t;
+        const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
+        for (uint32_t i = lane; i < len_l; i += 32) {
+            const uint32_t p = __ldg(sites + lo_l + i) - tile_base;
+            atomicOr(&bm[p >> 5], 1u << (p & 31));
+        }
+    }
+    __syncwarp();
+    uint32_t w[8];
+    {
+        uint4 *bm4 = reinterpret_cast<uint4 *>(bm) + 2 * lane;
+        const uint4 x = bm4[0], y = bm4[1];
+        bm4[0] = make_uint4(0, 0, 0, 0);
+        bm4[1] = make_uint4(0, 0, 0, 0);
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+    }
+    GapAcc acc;
+    acc.cnt = st.cnt; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
+    uint32_t enc = 0;                                          // (last position of my slice) + 1
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (w[q]) enc = tile_base + (lane * 8 + q) * 32 + (31 - __clz(w[q])) + 1;
+    uint32_t run = enc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d));
+    uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
+    if (lane == 0) pred = 0;
+    pred = max(pred, st.carry);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint32_t v = w[q];
+        const uint32_t wb = tile_base + (lane * 8 + q) * 32;
+        while (v) {
+            const uint32_t cur = wb + __ffs(v) - 1;
+            v &= v - 1;
+            if (pred) add_gap_r(acc, cur - (pred - 1), min(cur - (pred - 1), hist_bins), hist_s);
+            else st.first = cur + 1;
+            pred = cur + 1;
+        }
+    }
+    st.carry = max(st.carry, __shfl_sync(0xffffffffu, run, 31));
+    st.cnt = acc.cnt; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
+    __syncwarp();
+    return st;
+}
+
+template <bool ROUTED>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 k_score_dense(ScoreArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *bm_all = smem;                                               // [DT_WARPS][DT_WORDS]
-    uint16_t *cl_all = reinterpret_cast<uint16_t *>(bm_all + DT_WARPS * DT_WORDS);   // [DT_WARPS][DT_LIST_CAP]
-    uint32_t *hist = reinterpret_cast<uint32_t *>(cl_all + DT_WARPS * DT_LIST_CAP);  // [a.hist_bins]
+    // bitmap variant: [DT_WARPS][DT_LIST_CAP] compact lists (uint16) behind the bitmaps.  Routed variant: a warp's 1 KB is
+    // its 32 rows of DT_ROW_CAP uint16 AND the bitmap of dense_tile_slow (both are all-zero between uses)
+    uint16_t *cl_all = reinterpret_cast<uint16_t *>(bm_all + DT_WARPS * DT_WORDS);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(cl_all + (ROUTED ? 0u : DT_WARPS * DT_LIST_CAP));   // [a.hist_bins]
+    // routed variant: slots taken per window; the block is aligned so that `base | 4 * window` addresses a counter
+    __shared__ __align__(4096) uint32_t s_cnt[ROUTED ? DT_WARPS * 32 : 1];         // [warp][window]
+    __shared__ uint32_t s_dummy[ROUTED ? DT_WARPS * 32 : 1];                       // [warp][lane], see route_take
     __shared__ uint32_t s_list[SC_MAX_LISTS];
     __shared__ uint32_t s_nlists, s_set;
     __shared__ uint32_t s_first[DT_WARPS], s_last[DT_WARPS];              // (position + 1) of the first / last site of a warp's range
@@ -394,8 +539,18 @@ k_score_dense(ScoreArgs a)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t *bm = bm_all + warp * DT_WORDS;
-    const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + warp * DT_LIST_CAP);
+    const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + (ROUTED ? 0u : warp * DT_LIST_CAP));
     const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+    // routed variant: the row of window w is at 8 * (address of its counter) + rowc (counters: 128 B per warp, rows: 1 KB)
+    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(s_cnt + (ROUTED ? warp * 32 : 0));
+    const uint32_t rowc = bm_s - 8u * cnt_s;
+    const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + (ROUTED ? tid : 0));
+    const uint32_t dummy_bin = a.hist_bins + 1u + lane;                     // see add_gap_r
+    if constexpr (ROUTED) {
+        s_cnt[tid] = 0;
+        s_dummy[tid] = 0x40000000u;
+        if (tid == 0) hist[a.hist_bins] = 0;
+    }
     for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
@@ -461,6 +616,77 @@ k_score_dense(ScoreArgs a)
                     any = r[1] > r[0];
                 }
             }
+            if constexpr (ROUTED) {
+            if (any) {
+                bool slow = carry == 0u;                                   // no predecessor yet (warp-uniform)
+                uint4 row = make_uint4(0, 0, 0, 0), row2 = row;
+                uint32_t mx = 0;
+                if (!slow) {
+                    // ---- (2) every site takes a slot of its window's row ----
+                    const uint32_t kx = tile_base - 0x8000u;               // stored value = position - kx = rel | 0x8000
+                    {
+                        const uint32_t v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+                        const uint32_t first_idx = 8u * half - (lo & 3u);  // index in the segment of v[0] (may wrap below 0)
+                        uint32_t ca[8], old[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {                      // unsigned compare: also false before the segment
+                            ca[q] = cnt_s | ((v[q] >> 6) & 0x7Cu);         // tile_base is a multiple of 2^13: bits 8..12 = window
+                            old[q] = route_take(first_idx + q < len ? ca[q] : dummy_s);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) route_put(old[q], 8u * ca[q] + rowc, v[q] - kx);
+                    }
+                    while (need) {                                         // what the chunks do not cover
+                        const int l = __ffs(need) - 1;
+                        need &= need - 1;
+                        const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
+                        for (uint32_t i = 16u - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
+                            route_put(route_take(ca), 8u * ca + rowc, v - kx);
+                        }
+                    }
+                    for (uint32_t l = 16; l < nl; ++l) {                   // lists no lane owns
+                        const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
+                        const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
+                        for (uint32_t i = lane; i < len_l; i += 32) {
+                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
+                            route_put(route_take(ca), 8u * ca + rowc, v - kx);
+                        }
+                    }
+                    __syncwarp();
+                    // ---- (3) my window's count and row; both left empty for the next tile ----
+                    const uint32_t c = s_cnt[tid];
+                    s_cnt[tid] = 0;
+                    mx = __reduce_max_sync(0xffffffffu, c);                // most sites any window of the tile received
+                    uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;
+                    row = rowp[0];
+                    rowp[0] = make_uint4(0, 0, 0, 0);
+                    if (mx > 8u) {
+                        row2 = rowp[1];
+                        rowp[1] = make_uint4(0, 0, 0, 0);
+                    }
+                    slow = mx > DT_ROW_CAP;
+                    __syncwarp();
+                }
+                if (slow) {
+                    TileState st;
+                    st.carry = carry; st.first = first; st.cnt = 0; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
+                    st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, t, bm, hist_s, st);
+                    carry = st.carry; first = st.first; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
+                } else if (mx <= 8u) {
+                    // ---- (4) sort, gaps ----
+                    uint32_t v[8] = {row.x & 0xffffu, row.x >> 16, row.y & 0xffffu, row.y >> 16,
+                                     row.z & 0xffffu, row.z >> 16, row.w & 0xffffu, row.w >> 16};
+                    owner_gaps<8>(v, tile_base, lane, carry, acc, hist_s, a.hist_bins, dummy_bin);
+                } else {
+                    uint32_t v[16] = {row.x & 0xffffu, row.x >> 16, row.y & 0xffffu, row.y >> 16,
+                                      row.z & 0xffffu, row.z >> 16, row.w & 0xffffu, row.w >> 16,
+                                      row2.x & 0xffffu, row2.x >> 16, row2.y & 0xffffu, row2.y >> 16,
+                                      row2.z & 0xffffu, row2.z >> 16, row2.w & 0xffffu, row2.w >> 16};
+                    owner_gaps<16>(v, tile_base, lane, carry, acc, hist_s, a.hist_bins, dummy_bin);
+                }
+            }
+            } else {
             if (any) {
             // ---- (2) one bit per site ----
             {
@@ -565,6 +791,7 @@ k_score_dense(ScoreArgs a)
                 carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
             }
             }                                                              // if (any)
+            }                                                              // bitmap variant
             b0 = b1; b1 = b2; b2 = b3;
             pa = na; pb = nb4;
         }
@@ -580,14 +807,18 @@ k_score_dense(ScoreArgs a)
                 if (!s_last[wv]) continue;
                 if (prev) {
                     const uint32_t gap = s_first[wv] - prev;              // both carry the + 1
-                    add_gap(x, gap, hist_s, a.hist_bins);
+                    if constexpr (ROUTED) add_gap_r(x, gap, min(gap, a.hist_bins), hist_s);
+                    else add_gap(x, gap, hist_s, a.hist_bins);
                 }
                 prev = s_last[wv];
             }
             s_cross = x;
+            if constexpr (ROUTED) hist[0] = 0;                            // took the sites two lists share (add_gap_r)
         }
         __syncthreads();
-        const uint32_t n = block_reduce_dt(acc.cnt, OpAddU32(), 0u, s_red32) + s_cross.cnt;          // number of gaps
+        // number of gaps: counted per gap (bitmap variant) or the sum of the histogram incl. its overflow bin (routed)
+        uint32_t n = 0;
+        if constexpr (!ROUTED) n = block_reduce_dt(acc.cnt, OpAddU32(), 0u, s_red32) + s_cross.cnt;
         const uint32_t mx = max(block_reduce_dt(acc.maxgap, OpMaxU32(), 0u, s_red32), s_cross.maxgap);
         const unsigned long long ssq = block_reduce_dt(acc.sumsq, OpAddU64(), 0ull, s_red64) + s_cross.sumsq;
         const uint32_t fst1 = block_reduce_dt(first ? first : 0xffffffffu, OpMinU32(), 0xffffffffu, s_red32);
@@ -621,8 +852,10 @@ k_score_dense(ScoreArgs a)
                     if (lane >= (uint32_t)d) vi += o;
                 }
                 s_scan[lane] = vi - v;
+                if (lane == 31) s_scan[DT_WARPS] = vi;
             }
             __syncthreads();
+            if constexpr (ROUTED) n = s_scan[DT_WARPS] + hist[a.hist_bins];
             unsigned long long r = s_scan[warp] + inc - c_mine;               // gaps smaller than my first bin
             unsigned long long part = 0;
             for (uint32_t v = b0; v < b1; ++v) {
@@ -663,6 +896,7 @@ k_score_dense(ScoreArgs a)
             a.gini[s] = gini;
             a.score[s] = score;
             a.status[s] = (uint8_t)((passed ? 1 : 0) | ((!hist_ok) ? 2 : 0));
+            if constexpr (ROUTED) hist[a.hist_bins] = 0;
         }
         __syncthreads();
     }
@@ -1080,8 +1314,11 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         CUDA_TRY(cudaGetLastError());
     }
     // the rest: one warp per fine tile (k_score_dense)
-    const size_t smem = 4ull * DT_WARPS * DT_WORDS + 2ull * DT_WARPS * DT_LIST_CAP + 4ull * a.hist_bins;
-    CUDA_TRY(cudaFuncSetAttribute(k_score_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool routed = ctx->score_dense_impl == 0;
+    const size_t smem = 4ull * DT_WARPS * DT_WORDS + 2ull * DT_WARPS * (routed ? 0u : DT_LIST_CAP) +
+                        4ull * (a.hist_bins + (routed ? 33u : 0u));        // routed: + the overflow bin and 32 dummy words
+    CUDA_TRY(cudaFuncSetAttribute(routed ? k_score_dense<true> : k_score_dense<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = S < (uint32_t)ctx->sm_count ? S : (uint32_t)ctx->sm_count;
     if (a.sort_cap) {
         a.ids = ids + S;
@@ -1091,8 +1328,17 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         a.ids = ids + S;
         a.n_ids = n_ids + 1;
     }
-    SWGA_NOTE_LAUNCH(); k_score_dense<<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
+    SWGA_NOTE_LAUNCH();
+    if (routed) k_score_dense<true><<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
+    else k_score_dense<false><<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}
+
+extern "C" int swga_ctx_set_score_dense_impl(swga_ctx *ctx, int impl)
+{
+    ARG_CHECK(ctx && (impl == 0 || impl == 1));
+    ctx->score_dense_impl = impl;
     return SWGA_OK;
 }
 
