@@ -418,10 +418,11 @@ __device__ __forceinline__ void add_gap_r(GapAcc &acc, uint32_t g, uint32_t bin,
 }
 // The owner's half of a routed tile: v[] = the N values of my window's row (0 = empty slot).  Sorts them, then takes the
 // gap of every site to its predecessor: the register before it, or -- for the first site of the window -- the last
-// site before the window (running maximum over the lanes, `carry` from the tiles before; carry != 0 here).
-template <int N>
-__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base, uint32_t lane, uint32_t &carry, GapAcc &acc,
-                                           uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+// site before the window (running maximum over the lanes, `carry` from the tiles before).  FIRST: the tile may hold the
+// first site of the warp's range (carry == 0): that site has no gap and is reported in `first`.
+template <int N, bool FIRST>
+__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base, uint32_t lane, uint32_t &carry, uint32_t &first,
+                                           GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
 {
     // Batcher's odd-even merge sort, fully unrolled (every index is a compile-time constant)
 #pragma unroll
@@ -447,16 +448,37 @@ __device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base,
     for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d));
     uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
     if (lane == 0) pred = 0;
-    pred = max(pred, carry);                                   // >= 1: this tile has a predecessor
+    pred = max(pred, carry);                                   // >= 1 unless FIRST
     const uint32_t predrel = pred - K;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         // empty slot: g = 0 into my dummy word; a site two lists share: g = 0 into bin 0 (never read)
-        const uint32_t pv = (i && v[i ? i - 1 : 0]) ? v[i ? i - 1 : 0] : predrel;
-        const uint32_t g = v[i] ? v[i] - pv : 0u;
-        add_gap_r(acc, g, v[i] ? min(g, bins) : dummy_bin, hist_s);
+        const bool inlane = i && v[i ? i - 1 : 0];                 // the predecessor is the register before
+        const uint32_t pv = inlane ? v[i ? i - 1 : 0] : predrel;
+        bool site = v[i] != 0u;
+        if (FIRST && site && !inlane && pred == 0u) {
+            first = v[i] + K;
+            site = false;
+        }
+        const uint32_t g = site ? v[i] - pv : 0u;
+        add_gap_r(acc, g, site ? min(g, bins) : dummy_bin, hist_s);
     }
     carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
+}
+
+// owner_gaps on the first M slots of my window's row.  Slots fill in order, so when no window of the tile received more
+// than M sites the slots from M on are empty in EVERY lane: they are passed as literal zeros and the compiler drops
+// their compare-exchanges (min(x, 0) = 0, max(x, 0) = x) and their gap slots.
+template <int M, bool FIRST>
+__device__ __forceinline__ void owner_form(const uint4 &row, const uint4 &row2, uint32_t tile_base, uint32_t lane, uint32_t &carry,
+                                           uint32_t &first, GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+{
+    constexpr int N = M <= 8 ? 8 : 16;
+    const uint32_t w[8] = {row.x, row.y, row.z, row.w, row2.x, row2.y, row2.z, row2.w};
+    uint32_t v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = i < M ? ((i & 1) ? w[i >> 1] >> 16 : w[i >> 1] & 0xffffu) : 0u;
+    owner_gaps<N, FIRST>(v, tile_base, lane, carry, first, acc, hist_s, bins, dummy_bin);
 }
 
 // One tile through the bitmap, every lane walking its own 8 words (any number of sites, with or without a predecessor).
@@ -577,12 +599,13 @@ k_score_dense(ScoreArgs a)
         acc.cnt = 0; acc.maxgap = 0; acc.sumsq = 0;
         uint32_t carry = 0, first = 0;                                     // (position + 1); 0 = none yet
         const uint32_t t0 = min(a.n_tiles, warp * tpw), t1 = min(a.n_tiles, t0 + tpw);
-        // Software pipeline over the warp's tiles.  Lane = (list lane & 15, half lane >> 4): it reads two aligned
-        // 16-byte chunks of its list's segment of a tile (half 0: the chunks at aligned element offsets 0 and 4,
-        // half 1: 8 and 12), i.e. the first 13..16 sites of each of up to 16 lists in ONE load instruction per
-        // lane pair, one tile ahead (the loads of tile t + 1 fly while tile t is processed); the segment bounds
-        // are read two tiles ahead.  Longer segments and lists beyond 16 take the scalar loop below.
-        const uint32_t mylist = lane & 15u, half = lane >> 4;
+        // Software pipeline over the warp's tiles.  Lane = (list lane / L, part lane % L), L = 4, 3 or 2 lanes per list for up
+        // to 8, 10 or 16 lists: it reads two aligned 16-byte chunks of its list's segment of a tile (part p: the chunks at
+        // aligned element offsets 8 p and 8 p + 4), i.e. the first 8 L - 3 .. 8 L sites of every list in ONE load
+        // instruction per lane group, one tile ahead (the loads of tile t + 1 fly while tile t is processed); the segment
+        // bounds are read two tiles ahead.  Longer segments and lists beyond 16 take the scalar loop below.
+        const uint32_t L = nl <= 8 ? 4u : (nl <= 10 ? 3u : 2u);
+        const uint32_t mylist = lane / L, half = lane - mylist * L;
         const uint32_t *row = a.toff + (uint64_t)s_list[mylist < nl ? mylist : 0] * (a.n_tiles + 1);
         uint32_t b0 = 0, b1 = 0, b2 = 0;                                   // row[t], row[t + 1], row[t + 2] of my list
         if (mylist < nl && t0 < t1) {
@@ -607,9 +630,9 @@ k_score_dense(ScoreArgs a)
             }
             const uint32_t b3 = (mylist < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
             const uint32_t tile_base = t << DT_SHIFT;
-            const uint32_t covered = 16u - (lo & 3u);                      // sites of my list the chunks hold
+            const uint32_t covered = 8u * L - (lo & 3u);                   // sites of my list the chunks hold
             bool any = __any_sync(0xffffffffu, len != 0);
-            uint32_t need = __ballot_sync(0xffffffffu, len > covered) & 0xFFFFu;   // lists with sites beyond the chunks
+            uint32_t need = __ballot_sync(0xffffffffu, len > covered && half == 0u);   // lists (their first lane) with sites beyond the chunks
             if (nl > 16) {                                                 // lists no lane owns
                 for (uint32_t l = 16; l < nl && !any; ++l) {
                     const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
@@ -618,10 +641,11 @@ k_score_dense(ScoreArgs a)
             }
             if constexpr (ROUTED) {
             if (any) {
-                bool slow = carry == 0u;                                   // no predecessor yet (warp-uniform)
-                uint4 row = make_uint4(0, 0, 0, 0), row2 = row;
-                uint32_t mx = 0;
-                if (!slow) {
+                const bool nopred = carry == 0u;                           // no site yet in the warp's range (warp-uniform)
+                bool slow;
+                uint4 row, row2 = make_uint4(0, 0, 0, 0);
+                uint32_t mx;
+                {
                     // ---- (2) every site takes a slot of its window's row ----
                     const uint32_t kx = tile_base - 0x8000u;               // stored value = position - kx = rel | 0x8000
                     {
@@ -640,7 +664,7 @@ k_score_dense(ScoreArgs a)
                         const int l = __ffs(need) - 1;
                         need &= need - 1;
                         const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
-                        for (uint32_t i = 16u - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                        for (uint32_t i = 8u * L - (lo_l & 3u) + lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
                             route_put(route_take(ca), 8u * ca + rowc, v - kx);
                         }
@@ -661,7 +685,7 @@ k_score_dense(ScoreArgs a)
                     uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;
                     row = rowp[0];
                     rowp[0] = make_uint4(0, 0, 0, 0);
-                    if (mx > 8u) {
+                    if (mx > 8u || nopred) {
                         row2 = rowp[1];
                         rowp[1] = make_uint4(0, 0, 0, 0);
                     }
@@ -673,17 +697,22 @@ k_score_dense(ScoreArgs a)
                     st.carry = carry; st.first = first; st.cnt = 0; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
                     st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, t, bm, hist_s, st);
                     carry = st.carry; first = st.first; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
-                } else if (mx <= 8u) {
-                    // ---- (4) sort, gaps ----
-                    uint32_t v[8] = {row.x & 0xffffu, row.x >> 16, row.y & 0xffffu, row.y >> 16,
-                                     row.z & 0xffffu, row.z >> 16, row.w & 0xffffu, row.w >> 16};
-                    owner_gaps<8>(v, tile_base, lane, carry, acc, hist_s, a.hist_bins, dummy_bin);
+                } else if (nopred) {
+                    owner_form<16, true>(row, row2, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin);
                 } else {
-                    uint32_t v[16] = {row.x & 0xffffu, row.x >> 16, row.y & 0xffffu, row.y >> 16,
-                                      row.z & 0xffffu, row.z >> 16, row.w & 0xffffu, row.w >> 16,
-                                      row2.x & 0xffffu, row2.x >> 16, row2.y & 0xffffu, row2.y >> 16,
-                                      row2.z & 0xffffu, row2.z >> 16, row2.w & 0xffffu, row2.w >> 16};
-                    owner_gaps<16>(v, tile_base, lane, carry, acc, hist_s, a.hist_bins, dummy_bin);
+                    // ---- (4) sort, gaps: the form for the fullest window of the tile (warp-uniform) ----
+#define DT_FORM(M) owner_form<M, false>(row, row2, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin)
+                    if (mx <= 6u) {
+                        if (mx <= 4u) DT_FORM(4);
+                        else if (mx == 5u) DT_FORM(5);
+                        else DT_FORM(6);
+                    } else if (mx <= 8u) {
+                        if (mx == 7u) DT_FORM(7);
+                        else DT_FORM(8);
+                    } else if (mx <= 10u) DT_FORM(10);
+                    else if (mx <= 12u) DT_FORM(12);
+                    else DT_FORM(16);
+#undef DT_FORM
                 }
             }
             } else {
@@ -700,7 +729,7 @@ k_score_dense(ScoreArgs a)
                 const int l = __ffs(need) - 1;
                 need &= need - 1;
                 const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
-                for (uint32_t i = 16u - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                for (uint32_t i = 8u * L - (lo_l & 3u) + lane; i < len_l; i += 32) {
                     const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
                     atomicOr(&bm[p >> 5], 1u << (p & 31));
                 }
