@@ -147,8 +147,16 @@ __device__ __forceinline__ Group finish_group(const GenomeSrc &S, const RawGroup
         G.w0 = r.w0; G.w1 = r.w1; G.w2 = r.w2;
     } else {
         G.w0 = pack16(r.a); G.w1 = pack16(r.b);
-        uint32_t fa = 0;
-        if constexpr (SRC == SRC_ASCII_N) fa = flags16(r.a, SWGA_MASK_N);
+        // 'N' flags (DSK mode A).  Bit 3 of a byte is clear in A, C, G, T (either case) and set in 'N': the exact
+        // comparison (a third of this function's instructions) runs only when some lane of the warp holds such a byte.
+        uint32_t fa = 0, fb = 0;
+        if constexpr (SRC == SRC_ASCII_N) {
+            const uint32_t sus = (r.a.x | r.a.y | r.a.z | r.a.w | r.b.x | r.b.y | r.b.z | r.b.w) & 0x08080808u;
+            if (__any_sync(0xffffffffu, sus != 0u)) {
+                fa = flags16(r.a, SWGA_MASK_N);
+                fb = flags16(r.b, SWGA_MASK_N);
+            }
+        }
         uint32_t w2 = __shfl_down_sync(0xffffffffu, G.w0, 1), fc = __shfl_down_sync(0xffffffffu, fa, 1);
         if ((threadIdx.x & 31) == 31) {
             const uint64_t p = g * 32 + 32;
@@ -156,12 +164,15 @@ __device__ __forceinline__ Group finish_group(const GenomeSrc &S, const RawGroup
             if (n_starts != 0 && p + 16 <= S.n) c = ldg_nc_v4(S.ascii + p);
             else if (n_starts != 0 && p < S.n) c = ascii16_edge(S.ascii, p, S.n);
             w2 = pack16(c);
-            if constexpr (SRC == SRC_ASCII_N) fc = flags16(c, SWGA_MASK_N);
+            if constexpr (SRC == SRC_ASCII_N) {
+                fc = 0;
+                if ((c.x | c.y | c.z | c.w) & 0x08080808u) fc = flags16(c, SWGA_MASK_N);
+            }
         }
         G.w2 = w2;
         if constexpr (SRC == SRC_ASCII_N) {
             // an 'N' at base i forbids the windows over (i-1, i) and (i, i+1): brk[j] = bad[j] | bad[j+1]  (k_pack)
-            const uint32_t badA = (fa << 16) | flags16(r.b, SWGA_MASK_N);
+            const uint32_t badA = (fa << 16) | fb;
             const uint32_t badC = fc << 16;
             G.b0 |= badA | (badA << 1) | (badC >> 31);
             G.b1 |= badC | (badC << 1);                        // only its leading kmax-2 bits are looked at

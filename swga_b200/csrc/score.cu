@@ -402,10 +402,12 @@ __device__ __forceinline__ uint32_t route_take(uint32_t addr)
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
     return old;
 }
-__device__ __forceinline__ void route_put(uint32_t old, uint32_t row_addr, uint32_t x)
+// rows are slot-major: slot s of window w is the uint16 at 64 s + 2 w of the warp's 1 KB (the first slots of the 32
+// windows -- most stores -- fall on 16 different banks; a window-major row of 32 bytes would put them on 4)
+__device__ __forceinline__ void route_put(uint32_t old, uint32_t win_addr, uint32_t x)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 16;\n\t@p st.shared.u16 [%1], %2;\n\t}"
-                 ::"r"(old), "r"(row_addr + 2u * old), "h"((unsigned short)x) : "memory");
+                 ::"r"(old), "r"(win_addr + 64u * old), "h"((unsigned short)x) : "memory");
 }
 // Statistics of one gap in the routed kernel.  The histogram has one more bin behind the last (gaps >= hist_bins) and 32
 // dummy words behind that, one per lane, which take the increments of the empty register slots: the update is one
@@ -466,18 +468,20 @@ __device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base,
     carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
 }
 
-// owner_gaps on the first M slots of my window's row.  Slots fill in order, so when no window of the tile received more
-// than M sites the slots from M on are empty in EVERY lane: they are passed as literal zeros and the compiler drops
-// their compare-exchanges (min(x, 0) = 0, max(x, 0) = x) and their gap slots.
+// owner_gaps on the first M slots of my window (read and left empty here; `win_s` = address of my slot 0).  Slots fill in
+// order, so when no window of the tile received more than M sites the slots from M on are empty in EVERY lane: they are
+// passed as literal zeros and the compiler drops their compare-exchanges (min(x, 0) = 0, max(x, 0) = x) and gap slots.
 template <int M, bool FIRST>
-__device__ __forceinline__ void owner_form(const uint4 &row, const uint4 &row2, uint32_t tile_base, uint32_t lane, uint32_t &carry,
-                                           uint32_t &first, GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+__device__ __forceinline__ void owner_form(uint32_t win_s, uint32_t tile_base, uint32_t lane, uint32_t &carry, uint32_t &first,
+                                           GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
 {
     constexpr int N = M <= 8 ? 8 : 16;
-    const uint32_t w[8] = {row.x, row.y, row.z, row.w, row2.x, row2.y, row2.z, row2.w};
     uint32_t v[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = i < M ? ((i & 1) ? w[i >> 1] >> 16 : w[i >> 1] & 0xffffu) : 0u;
+    for (int i = 0; i < N; ++i) v[i] = i < M ? lds_u16(win_s + 64u * i) : 0u;
+#pragma unroll
+    for (int i = 0; i < M; ++i) sts_u16(win_s + 64u * i, 0u);
+    __syncwarp();
     owner_gaps<N, FIRST>(v, tile_base, lane, carry, first, acc, hist_s, bins, dummy_bin);
 }
 
@@ -563,9 +567,9 @@ k_score_dense(ScoreArgs a)
     uint32_t *bm = bm_all + warp * DT_WORDS;
     const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + (ROUTED ? 0u : warp * DT_LIST_CAP));
     const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-    // routed variant: the row of window w is at 8 * (address of its counter) + rowc (counters: 128 B per warp, rows: 1 KB)
+    // routed variant: slot 0 of window w is at (address of its counter) / 2 + rowc (counters: 128 B per warp, 128-byte aligned)
     const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(s_cnt + (ROUTED ? warp * 32 : 0));
-    const uint32_t rowc = bm_s - 8u * cnt_s;
+    const uint32_t rowc = bm_s - (cnt_s >> 1);
     const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + (ROUTED ? tid : 0));
     const uint32_t dummy_bin = a.hist_bins + 1u + lane;                     // see add_gap_r
     if constexpr (ROUTED) {
@@ -643,7 +647,6 @@ k_score_dense(ScoreArgs a)
             if (any) {
                 const bool nopred = carry == 0u;                           // no site yet in the warp's range (warp-uniform)
                 bool slow;
-                uint4 row, row2 = make_uint4(0, 0, 0, 0);
                 uint32_t mx;
                 {
                     // ---- (2) every site takes a slot of its window's row ----
@@ -658,7 +661,7 @@ k_score_dense(ScoreArgs a)
                             old[q] = route_take(first_idx + q < len ? ca[q] : dummy_s);
                         }
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) route_put(old[q], 8u * ca[q] + rowc, v[q] - kx);
+                        for (int q = 0; q < 8; ++q) route_put(old[q], (ca[q] >> 1) + rowc, v[q] - kx);
                     }
                     while (need) {                                         // what the chunks do not cover
                         const int l = __ffs(need) - 1;
@@ -666,7 +669,7 @@ k_score_dense(ScoreArgs a)
                         const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
                         for (uint32_t i = 8u * L - (lo_l & 3u) + lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
-                            route_put(route_take(ca), 8u * ca + rowc, v - kx);
+                            route_put(route_take(ca), (ca >> 1) + rowc, v - kx);
                         }
                     }
                     for (uint32_t l = 16; l < nl; ++l) {                   // lists no lane owns
@@ -674,34 +677,31 @@ k_score_dense(ScoreArgs a)
                         const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
                         for (uint32_t i = lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
-                            route_put(route_take(ca), 8u * ca + rowc, v - kx);
+                            route_put(route_take(ca), (ca >> 1) + rowc, v - kx);
                         }
                     }
                     __syncwarp();
-                    // ---- (3) my window's count and row; both left empty for the next tile ----
+                    // ---- (3) my window's count (left at 0 for the next tile) ----
                     const uint32_t c = s_cnt[tid];
                     s_cnt[tid] = 0;
                     mx = __reduce_max_sync(0xffffffffu, c);                // most sites any window of the tile received
-                    uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;
-                    row = rowp[0];
-                    rowp[0] = make_uint4(0, 0, 0, 0);
-                    if (mx > 8u || nopred) {
-                        row2 = rowp[1];
-                        rowp[1] = make_uint4(0, 0, 0, 0);
-                    }
                     slow = mx > DT_ROW_CAP;
-                    __syncwarp();
                 }
+                const uint32_t win_s = bm_s + 2u * lane;
                 if (slow) {
+                    uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;   // the rows become the bitmap: all 16 slots were filled
+                    rowp[0] = make_uint4(0, 0, 0, 0);
+                    rowp[1] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
                     TileState st;
                     st.carry = carry; st.first = first; st.cnt = 0; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
                     st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, t, bm, hist_s, st);
                     carry = st.carry; first = st.first; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
                 } else if (nopred) {
-                    owner_form<16, true>(row, row2, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin);
+                    owner_form<16, true>(win_s, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin);
                 } else {
-                    // ---- (4) sort, gaps: the form for the fullest window of the tile (warp-uniform) ----
-#define DT_FORM(M) owner_form<M, false>(row, row2, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin)
+                    // ---- (4) my window's slots; sort, gaps: the form for the fullest window of the tile (warp-uniform) ----
+#define DT_FORM(M) owner_form<M, false>(win_s, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin)
                     if (mx <= 6u) {
                         if (mx <= 4u) DT_FORM(4);
                         else if (mx == 5u) DT_FORM(5);

@@ -247,6 +247,9 @@ def test_scoring_kernels_edge_shapes(oracle):
     for n in (9000, 20000, 50000):                                                 # ordinary dense lists
         lists.append(np.sort(rng.choice(L, n, replace=False)))
     lists.append(lists[-1][::2].copy())                                            # shares every position with another list
+    # the routed dense kernel picks its form by the fullest 256-position window of a tile: 6-7, 12-13, 15-16, 17-18 sites
+    for step in (40, 20, 16, 15):
+        lists.append(np.arange(1_200_000 + 100_000 * (step % 7), 1_200_000 + 100_000 * (step % 7) + 60_000, step))
     while len(lists) < 34:
         lists.append(np.sort(rng.choice(L, int(rng.randint(3000, 9000)), replace=False)))
     sl = score.SiteLists.from_host_lists(lists, bounds, L)
@@ -257,7 +260,8 @@ def test_scoring_kernels_edge_shapes(oracle):
         sets.append([i])                                                           # one sparse list + bounds
     sets += [[0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10, 11, 12, 13], [13], [11, 13], [14], [15], [14, 15, 16], [16],
              [17, 18, 19, 20], [19, 20], list(range(14, 34)), list(range(3, 34)), list(range(0, 31)),
-             [21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 17, 18, 19, 14]]
+             [21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 17, 18, 19, 14], [22], [23], [24], [25], [22, 23, 24, 25],
+             [21, 22], [0, 24]]
     for _ in range(25):
         m = int(rng.randint(1, max_m + 1))
         sets.append(list(rng.choice(P_, m, replace=False)))
@@ -267,8 +271,10 @@ def test_scoring_kernels_edge_shapes(oracle):
     bgs = rng.uniform(10, 1e4, len(sets))
     lib, ctx = _lib.load(), _lib.context(0)
     try:
-        for cap in (4096, 0, 64, 16384):
+        # sort cap x dense-kernel form: (0, 1) = every set through the bitmap form of round 1, the rest the routed form
+        for cap, dense_impl in ((4096, 0), (0, 0), (0, 1), (64, 0), (16384, 0)):
             _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, cap))
+            _lib.check(lib.swga_ctx_set_score_dense_impl(ctx.h, dense_impl))
             for max_fg in (36000, 2 ** 31 - 1):
                 res = score.score_sets(sl, arr, bgs, max_fg)
                 for i, s in enumerate(sets):
@@ -283,6 +289,7 @@ def test_scoring_kernels_edge_shapes(oracle):
                         assert float(res.fg_dist_gini[i]) == oracle.gini(gaps), (cap, i)
     finally:
         _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
+        _lib.check(lib.swga_ctx_set_score_dense_impl(ctx.h, 0))
 
 
 def test_config3_config4_full_size(oracle):
