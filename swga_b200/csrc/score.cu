@@ -609,7 +609,9 @@ k_score_dense(ScoreArgs a)
         // instruction per lane group, one tile ahead (the loads of tile t + 1 fly while tile t is processed); the segment
         // bounds are read two tiles ahead.  Longer segments and lists beyond 16 take the scalar loop below.
         const uint32_t L = nl <= 8 ? 4u : (nl <= 10 ? 3u : 2u);
-        const uint32_t mylist = lane / L, half = lane - mylist * L;
+        const uint32_t mylist = lane / L;
+        uint32_t half = lane - mylist * L, cov8 = 8u * L;
+        asm volatile("" : "+r"(half), "+r"(cov8));                       // kept in registers: the compiler otherwise recomputes both per tile
         const uint32_t *row = a.toff + (uint64_t)s_list[mylist < nl ? mylist : 0] * (a.n_tiles + 1);
         uint32_t b0 = 0, b1 = 0, b2 = 0;                                   // row[t], row[t + 1], row[t + 2] of my list
         if (mylist < nl && t0 < t1) {
@@ -634,7 +636,7 @@ k_score_dense(ScoreArgs a)
             }
             const uint32_t b3 = (mylist < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
             const uint32_t tile_base = t << DT_SHIFT;
-            const uint32_t covered = 8u * L - (lo & 3u);                   // sites of my list the chunks hold
+            const uint32_t covered = cov8 - (lo & 3u);                   // sites of my list the chunks hold
             bool any = __any_sync(0xffffffffu, len != 0);
             uint32_t need = __ballot_sync(0xffffffffu, len > covered && half == 0u);   // lists (their first lane) with sites beyond the chunks
             if (nl > 16) {                                                 // lists no lane owns
@@ -653,12 +655,14 @@ k_score_dense(ScoreArgs a)
                     const uint32_t kx = tile_base - 0x8000u;               // stored value = position - kx = rel | 0x8000
                     {
                         const uint32_t v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-                        const uint32_t first_idx = 8u * half - (lo & 3u);  // index in the segment of v[0] (may wrap below 0)
+                        // entry q of my chunks is site number 8 half - (lo & 3) + q of the segment: a site for qlo <= q < qhi
+                        const int qlo = half ? 0 : (int)(lo & 3u), qhi = (int)len - (int)(8u * half) + (int)(lo & 3u);
                         uint32_t ca[8], old[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {                      // unsigned compare: also false before the segment
+                        for (int q = 0; q < 8; ++q) {
                             ca[q] = cnt_s | ((v[q] >> 6) & 0x7Cu);         // tile_base is a multiple of 2^13: bits 8..12 = window
-                            old[q] = route_take(first_idx + q < len ? ca[q] : dummy_s);
+                            const bool site = q < 3 ? (q >= qlo && q < qhi) : q < qhi;   // qlo <= 3
+                            old[q] = route_take(site ? ca[q] : dummy_s);
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) route_put(old[q], (ca[q] >> 1) + rowc, v[q] - kx);
@@ -667,7 +671,7 @@ k_score_dense(ScoreArgs a)
                         const int l = __ffs(need) - 1;
                         need &= need - 1;
                         const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
-                        for (uint32_t i = 8u * L - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                        for (uint32_t i = cov8 - (lo_l & 3u) + lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
                             route_put(route_take(ca), (ca >> 1) + rowc, v - kx);
                         }
@@ -729,7 +733,7 @@ k_score_dense(ScoreArgs a)
                 const int l = __ffs(need) - 1;
                 need &= need - 1;
                 const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
-                for (uint32_t i = 8u * L - (lo_l & 3u) + lane; i < len_l; i += 32) {
+                for (uint32_t i = cov8 - (lo_l & 3u) + lane; i < len_l; i += 32) {
                     const uint32_t p = __ldg(a.sites + lo_l + i) - tile_base;
                     atomicOr(&bm[p >> 5], 1u << (p & 31));
                 }
