@@ -382,16 +382,20 @@ __device__ __forceinline__ void set_bit_if(uint32_t idx, uint32_t len, uint32_t 
 // ---- routed variant of the dense kernel (default) ------------------------------------------------------
 // The bitmap variant spends 60 % of its instructions on divergent bit-extraction loops and the gap pass that follows
 // them (profiles/r01_summary.md).  Here a tile is a per-warp COUNTING SORT instead: lane w owns the window of 256
-// positions [256 w, 256 w + 256) of the tile; every site takes the next slot of its window's 32-byte row with one
-// shared atomicAdd (its value, tile-relative | 0x8000, goes there as uint16); the owner reads its row with 16-byte
-// loads, clears it, sorts the values in registers (Batcher's network: 19 compare-exchanges for 8 values, 63 for 16;
-// empty slots are 0 and sort to the front) and takes the gaps from neighbouring registers -- straight-line predicated
-// code, no loop whose trip count differs between lanes.  The predecessor of a window's first site is the running
-// maximum of the windows before it (one warp scan).  The warp takes the 8-value form when no window of the tile
-// received more than 8 sites (89 % of the C4-dense tiles), the 16-value form up to 16, and dense_tile_slow() --
-// bitmap + per-lane bit walk, in the same shared memory as the rows -- beyond that or when the tile has no predecessor
-// (the first non-empty tile of a warp's range).
+// positions [256 w, 256 w + 256) of the tile; every site takes the next slot of its window with one shared atomicAdd
+// on the window's counter and is stored there as it is (a 32-bit position); the owner reads its slots, leaves them
+// empty (0xffffffff), sorts the values in registers (Batcher's network: 19 compare-exchanges for 8 values, 63 for 16;
+// empty slots sort to the end) and takes the gaps from neighbouring registers -- straight-line predicated code, no
+// loop whose trip count differs between lanes.  The predecessor of a window's first site is the running maximum of
+// the windows before it (one warp scan).  The warp takes the form for the fullest window of the tile (4 .. 16 live
+// slots; 89 % of the C4-dense tiles need at most 8) and dense_tile_slow() -- bitmap + per-lane bit walk, in the
+// shared memory of the slots -- beyond 16.
+// Shared memory of a warp (DT_RT_BYTES, 128-byte aligned): [32 counters][slot 0 of the 32 windows][slot 1] ... [slot 15],
+// so that the address of slot s of a window is (address of its counter) + 128 (s + 1): one LEA after the atomic, and
+// the stores of a slot index fall on 32 different banks.
 #define DT_ROW_CAP 16u
+#define DT_RT_BYTES (128u * (DT_ROW_CAP + 1u))
+#define DT_EMPTY 0xffffffffu
 
 // Slot of a chunk entry in its window's row.  Branch-free: the atomic of an entry that is not a site of the segment goes to
 // a per-lane dummy counter that starts at 2^30 (a predicated atomic compiles to a branch with a reconvergence barrier
@@ -402,12 +406,20 @@ __device__ __forceinline__ uint32_t route_take(uint32_t addr)
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
     return old;
 }
-// rows are slot-major: slot s of window w is the uint16 at 64 s + 2 w of the warp's 1 KB (the first slots of the 32
-// windows -- most stores -- fall on 16 different banks; a window-major row of 32 bytes would put them on 4)
-__device__ __forceinline__ void route_put(uint32_t old, uint32_t win_addr, uint32_t x)
+__device__ __forceinline__ void route_put(uint32_t old, uint32_t cnt_addr, uint32_t v)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 16;\n\t@p st.shared.u16 [%1], %2;\n\t}"
-                 ::"r"(old), "r"(win_addr + 64u * old), "h"((unsigned short)x) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 16;\n\t@p st.shared.u32 [%1+128], %2;\n\t}"
+                 ::"r"(old), "r"(cnt_addr + 128u * old), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 // Statistics of one gap in the routed kernel.  The histogram has one more bin behind the last (gaps >= hist_bins) and 32
 // dummy words behind that, one per lane, which take the increments of the empty register slots: the update is one
@@ -418,15 +430,27 @@ __device__ __forceinline__ void add_gap_r(GapAcc &acc, uint32_t g, uint32_t bin,
     acc.maxgap = max(acc.maxgap, g);
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * bin) : "memory");
 }
-// The owner's half of a routed tile: v[] = the N values of my window's row (0 = empty slot).  Sorts them, then takes the
-// gap of every site to its predecessor: the register before it, or -- for the first site of the window -- the last
-// site before the window (running maximum over the lanes, `carry` from the tiles before).  FIRST: the tile may hold the
-// first site of the warp's range (carry == 0): that site has no gap and is reported in `first`.
-template <int N, bool FIRST>
-__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base, uint32_t lane, uint32_t &carry, uint32_t &first,
-                                           GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+// The owner's half of a routed tile: v[0 .. M) = the slots of my window (DT_EMPTY = empty; v[M .. N) are not looked at: no
+// window of the tile received more than M sites and slots fill in order).  Sorts them ascending -- the sites then
+// come first -- and takes the gap of every site to its predecessor: the register before it, or, for the first, the
+// last site before the window (running maximum over the lanes, `carry` from the tiles before, both as position + 1).
+// FIRST: the tile may hold the first site of the warp's range (carry == 0): that site has no gap and is reported.
+template <int N, int M, bool FIRST>
+__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t lane, uint32_t &carry, uint32_t &first, GapAcc &acc,
+                                           uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
 {
-    // Batcher's odd-even merge sort, fully unrolled (every index is a compile-time constant)
+    // (last position of my window) + 1, 0 = no site: the largest v + 1 (an empty slot wraps to 0), taken from the UNSORTED
+    // values so that the warp scan below does not wait for the sorting network
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) run = max(run, v[i] + 1u);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d));
+    uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
+    if (lane == 0) pred = 0;
+    pred = max(pred, carry);                                   // >= 1 unless FIRST
+    // Batcher's odd-even merge sort of N = 8 or 16 inputs, fully unrolled (every index is a compile-time constant); the
+    // inputs from M on count as +infinity, so a compare-exchange that touches one of them does nothing and is left out
 #pragma unroll
     for (int p = 1; p < N; p <<= 1) {
 #pragma unroll
@@ -435,7 +459,7 @@ __device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base,
             for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
 #pragma unroll
                 for (int i = 0; i <= (k - 1 < N - j - k - 1 ? k - 1 : N - j - k - 1); ++i) {
-                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p) && i + j + k < M) {
                         const uint32_t lo_ = min(v[i + j], v[i + j + k]), hi_ = max(v[i + j], v[i + j + k]);
                         v[i + j] = lo_;
                         v[i + j + k] = hi_;
@@ -444,45 +468,33 @@ __device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t tile_base,
             }
         }
     }
-    const uint32_t K = tile_base - 0x8000u + 1u;               // stored value + K = position + 1
-    uint32_t run = v[N - 1] ? v[N - 1] + K : 0u;               // (last position of my window) + 1
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) run = max(run, __shfl_up_sync(0xffffffffu, run, d));
-    uint32_t pred = __shfl_up_sync(0xffffffffu, run, 1);
-    if (lane == 0) pred = 0;
-    pred = max(pred, carry);                                   // >= 1 unless FIRST
-    const uint32_t predrel = pred - K;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        // empty slot: g = 0 into my dummy word; a site two lists share: g = 0 into bin 0 (never read)
-        const bool inlane = i && v[i ? i - 1 : 0];                 // the predecessor is the register before
-        const uint32_t pv = inlane ? v[i ? i - 1 : 0] : predrel;
-        bool site = v[i] != 0u;
-        if (FIRST && site && !inlane && pred == 0u) {
-            first = v[i] + K;
+    for (int i = 0; i < M; ++i) {
+        // empty slot: into my dummy word; a site two lists share: g = 0 into bin 0 (never read)
+        bool site = v[i] != DT_EMPTY;
+        if (FIRST && i == 0 && site && pred == 0u) {
+            first = v[0] + 1u;
             site = false;
         }
-        const uint32_t g = site ? v[i] - pv : 0u;
+        const uint32_t g = site ? (i ? v[i] - v[i ? i - 1 : 0] : v[0] + 1u - pred) : 0u;
         add_gap_r(acc, g, site ? min(g, bins) : dummy_bin, hist_s);
     }
     carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
 }
 
-// owner_gaps on the first M slots of my window (read and left empty here; `win_s` = address of my slot 0).  Slots fill in
-// order, so when no window of the tile received more than M sites the slots from M on are empty in EVERY lane: they are
-// passed as literal zeros and the compiler drops their compare-exchanges (min(x, 0) = 0, max(x, 0) = x) and gap slots.
+// owner_gaps on the first M slots of my window (read and left empty here; `win_s` = address of my slot 0)
 template <int M, bool FIRST>
-__device__ __forceinline__ void owner_form(uint32_t win_s, uint32_t tile_base, uint32_t lane, uint32_t &carry, uint32_t &first,
-                                           GapAcc &acc, uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+__device__ __forceinline__ void owner_form(uint32_t win_s, uint32_t lane, uint32_t &carry, uint32_t &first, GapAcc &acc,
+                                           uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
 {
     constexpr int N = M <= 8 ? 8 : 16;
     uint32_t v[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = i < M ? lds_u16(win_s + 64u * i) : 0u;
+    for (int i = 0; i < N; ++i) v[i] = i < M ? lds_u32(win_s + 128u * i) : DT_EMPTY;
 #pragma unroll
-    for (int i = 0; i < M; ++i) sts_u16(win_s + 64u * i, 0u);
+    for (int i = 0; i < M; ++i) sts_u32(win_s + 128u * i, DT_EMPTY);
     __syncwarp();
-    owner_gaps<N, FIRST>(v, tile_base, lane, carry, first, acc, hist_s, bins, dummy_bin);
+    owner_gaps<N, M, FIRST>(v, lane, carry, first, acc, hist_s, bins, dummy_bin);
 }
 
 // One tile through the bitmap, every lane walking its own 8 words (any number of sites, with or without a predecessor).
@@ -548,13 +560,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1)
 k_score_dense(ScoreArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *bm_all = smem;                                               // [DT_WARPS][DT_WORDS]
-    // bitmap variant: [DT_WARPS][DT_LIST_CAP] compact lists (uint16) behind the bitmaps.  Routed variant: a warp's 1 KB is
-    // its 32 rows of DT_ROW_CAP uint16 AND the bitmap of dense_tile_slow (both are all-zero between uses)
-    uint16_t *cl_all = reinterpret_cast<uint16_t *>(bm_all + DT_WARPS * DT_WORDS);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(cl_all + (ROUTED ? 0u : DT_WARPS * DT_LIST_CAP));   // [a.hist_bins]
-    // routed variant: slots taken per window; the block is aligned so that `base | 4 * window` addresses a counter
-    __shared__ __align__(4096) uint32_t s_cnt[ROUTED ? DT_WARPS * 32 : 1];         // [warp][window]
     __shared__ uint32_t s_dummy[ROUTED ? DT_WARPS * 32 : 1];                       // [warp][lane], see route_take
     __shared__ uint32_t s_list[SC_MAX_LISTS];
     __shared__ uint32_t s_nlists, s_set;
@@ -564,20 +569,32 @@ k_score_dense(ScoreArgs a)
     __shared__ GapAcc s_cross;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *bm = bm_all + warp * DT_WORDS;
-    const uint32_t cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + (ROUTED ? 0u : warp * DT_LIST_CAP));
-    const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-    // routed variant: slot 0 of window w is at (address of its counter) / 2 + rowc (counters: 128 B per warp, 128-byte aligned)
-    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(s_cnt + (ROUTED ? warp * 32 : 0));
-    const uint32_t rowc = bm_s - (cnt_s >> 1);
-    const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + (ROUTED ? tid : 0));
-    const uint32_t dummy_bin = a.hist_bins + 1u + lane;                     // see add_gap_r
+    // bitmap variant: [DT_WARPS][DT_WORDS] bitmaps, [DT_WARPS][DT_LIST_CAP] compact lists (uint16), histogram.
+    // routed variant: [DT_WARPS][DT_RT_BYTES] counters + slots from the next 128-byte boundary, histogram; the first 1 KB
+    // of a warp's slots is also the bitmap of dense_tile_slow
+    uint32_t *bm, *hist;
+    uint32_t cl_s = 0, cnt_s = 0;
     if constexpr (ROUTED) {
-        s_cnt[tid] = 0;
+        const uint32_t pad = (128u - ((uint32_t)__cvta_generic_to_shared(smem) & 127u)) & 127u;
+        uint8_t *rt0 = reinterpret_cast<uint8_t *>(smem) + pad, *rt = rt0 + warp * DT_RT_BYTES;
+        cnt_s = (uint32_t)__cvta_generic_to_shared(rt);
+        bm = reinterpret_cast<uint32_t *>(rt + 128);
+        hist = reinterpret_cast<uint32_t *>(rt0 + DT_WARPS * DT_RT_BYTES);
+        reinterpret_cast<uint32_t *>(rt)[lane] = 0;
+        for (uint32_t i = 0; i < DT_ROW_CAP; ++i) bm[i * 32 + lane] = DT_EMPTY;
         s_dummy[tid] = 0x40000000u;
         if (tid == 0) hist[a.hist_bins] = 0;
+    } else {
+        uint32_t *bm_all = smem;
+        uint16_t *cl_all = reinterpret_cast<uint16_t *>(bm_all + DT_WARPS * DT_WORDS);
+        bm = bm_all + warp * DT_WORDS;
+        hist = reinterpret_cast<uint32_t *>(cl_all + DT_WARPS * DT_LIST_CAP);
+        cl_s = (uint32_t)__cvta_generic_to_shared(cl_all + warp * DT_LIST_CAP);
+        for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
     }
-    for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
+    const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+    const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + (ROUTED ? tid : 0));
+    const uint32_t dummy_bin = a.hist_bins + 1u + lane;                     // see add_gap_r
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
 
@@ -651,8 +668,7 @@ k_score_dense(ScoreArgs a)
                 bool slow;
                 uint32_t mx;
                 {
-                    // ---- (2) every site takes a slot of its window's row ----
-                    const uint32_t kx = tile_base - 0x8000u;               // stored value = position - kx = rel | 0x8000
+                    // ---- (2) every site takes a slot of its window ----
                     {
                         const uint32_t v[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
                         // entry q of my chunks is site number 8 half - (lo & 3) + q of the segment: a site for qlo <= q < qhi
@@ -665,7 +681,7 @@ k_score_dense(ScoreArgs a)
                             old[q] = route_take(site ? ca[q] : dummy_s);
                         }
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) route_put(old[q], (ca[q] >> 1) + rowc, v[q] - kx);
+                        for (int q = 0; q < 8; ++q) route_put(old[q], ca[q], v[q]);
                     }
                     while (need) {                                         // what the chunks do not cover
                         const int l = __ffs(need) - 1;
@@ -673,7 +689,7 @@ k_score_dense(ScoreArgs a)
                         const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
                         for (uint32_t i = cov8 - (lo_l & 3u) + lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
-                            route_put(route_take(ca), (ca >> 1) + rowc, v - kx);
+                            route_put(route_take(ca), ca, v);
                         }
                     }
                     for (uint32_t l = 16; l < nl; ++l) {                   // lists no lane owns
@@ -681,19 +697,21 @@ k_score_dense(ScoreArgs a)
                         const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
                         for (uint32_t i = lane; i < len_l; i += 32) {
                             const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
-                            route_put(route_take(ca), (ca >> 1) + rowc, v - kx);
+                            route_put(route_take(ca), ca, v);
                         }
                     }
                     __syncwarp();
                     // ---- (3) my window's count (left at 0 for the next tile) ----
-                    const uint32_t c = s_cnt[tid];
-                    s_cnt[tid] = 0;
+                    const uint32_t c = lds_u32(cnt_s + 4u * lane);
+                    sts_u32(cnt_s + 4u * lane, 0u);
                     mx = __reduce_max_sync(0xffffffffu, c);                // most sites any window of the tile received
                     slow = mx > DT_ROW_CAP;
                 }
-                const uint32_t win_s = bm_s + 2u * lane;
+                const uint32_t win_s = cnt_s + 128u + 4u * lane;
                 if (slow) {
-                    uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;   // the rows become the bitmap: all 16 slots were filled
+                    // the first 1 KB of the slots becomes the bitmap (all 16 slots of a window may hold sites); afterwards
+                    // every slot is empty again
+                    uint4 *rowp = reinterpret_cast<uint4 *>(bm) + 2 * lane;
                     rowp[0] = make_uint4(0, 0, 0, 0);
                     rowp[1] = make_uint4(0, 0, 0, 0);
                     __syncwarp();
@@ -701,11 +719,15 @@ k_score_dense(ScoreArgs a)
                     st.carry = carry; st.first = first; st.cnt = 0; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
                     st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, t, bm, hist_s, st);
                     carry = st.carry; first = st.first; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
+                    uint4 *all = reinterpret_cast<uint4 *>(bm) + 4 * lane;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) all[i] = make_uint4(DT_EMPTY, DT_EMPTY, DT_EMPTY, DT_EMPTY);
+                    __syncwarp();
                 } else if (nopred) {
-                    owner_form<16, true>(win_s, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin);
+                    owner_form<16, true>(win_s, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin);
                 } else {
                     // ---- (4) my window's slots; sort, gaps: the form for the fullest window of the tile (warp-uniform) ----
-#define DT_FORM(M) owner_form<M, false>(win_s, tile_base, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin)
+#define DT_FORM(M) owner_form<M, false>(win_s, lane, carry, first, acc, hist_s, a.hist_bins, dummy_bin)
                     if (mx <= 6u) {
                         if (mx <= 4u) DT_FORM(4);
                         else if (mx == 5u) DT_FORM(5);
@@ -1348,8 +1370,14 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
     }
     // the rest: one warp per fine tile (k_score_dense)
     const bool routed = ctx->score_dense_impl == 0;
-    const size_t smem = 4ull * DT_WARPS * DT_WORDS + 2ull * DT_WARPS * (routed ? 0u : DT_LIST_CAP) +
-                        4ull * (a.hist_bins + (routed ? 33u : 0u));        // routed: + the overflow bin and 32 dummy words
+    // routed: alignment slack + counters and slots + histogram with its overflow bin and 32 dummy words; the histogram of
+    // the dense kernel is what fits beside them (sets with a larger gap are flagged for swga_gini_unbounded as always)
+    if (routed) {
+        const uint32_t fit = (uint32_t)((227u * 1024u - 6144u - 128u - DT_WARPS * DT_RT_BYTES) / 4u - 33u);   // 39,103
+        a.hist_bins = std::min(a.hist_bins, fit);
+    }
+    const size_t smem = routed ? 128ull + (size_t)DT_WARPS * DT_RT_BYTES + 4ull * (a.hist_bins + 33u)
+                               : 4ull * DT_WARPS * DT_WORDS + 2ull * DT_WARPS * DT_LIST_CAP + 4ull * a.hist_bins;
     CUDA_TRY(cudaFuncSetAttribute(routed ? k_score_dense<true> : k_score_dense<false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = S < (uint32_t)ctx->sm_count ? S : (uint32_t)ctx->sm_count;
