@@ -397,9 +397,9 @@ __device__ __forceinline__ void set_bit_if(uint32_t idx, uint32_t len, uint32_t 
 #define DT_RT_BYTES (128u * (DT_ROW_CAP + 1u))
 #define DT_EMPTY 0xffffffffu
 
-// Slot of a chunk entry in its window's row.  Branch-free: the atomic of an entry that is not a site of the segment goes to
-// a per-lane dummy counter that starts at 2^30 (a predicated atomic compiles to a branch with a reconvergence barrier
-// around it), so its "slot" is never below DT_ROW_CAP and its store is predicated off like that of a 17th site.
+// The next slot of a window: one shared atomicAdd on its counter.  Chunk entries that are not sites of the segment skip
+// it by a branch (a predicated atomic compiles to a branch anyway); their "slot" is DT_ROW_CAP, which predicates the
+// store off like that of a 17th site.
 __device__ __forceinline__ uint32_t route_take(uint32_t addr)
 {
     uint32_t old;
@@ -560,7 +560,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1)
 k_score_dense(ScoreArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_dummy[ROUTED ? DT_WARPS * 32 : 1];                       // [warp][lane], see route_take
     __shared__ uint32_t s_list[SC_MAX_LISTS];
     __shared__ uint32_t s_nlists, s_set;
     __shared__ uint32_t s_first[DT_WARPS], s_last[DT_WARPS];              // (position + 1) of the first / last site of a warp's range
@@ -582,7 +581,6 @@ k_score_dense(ScoreArgs a)
         hist = reinterpret_cast<uint32_t *>(rt0 + DT_WARPS * DT_RT_BYTES);
         reinterpret_cast<uint32_t *>(rt)[lane] = 0;
         for (uint32_t i = 0; i < DT_ROW_CAP; ++i) bm[i * 32 + lane] = DT_EMPTY;
-        s_dummy[tid] = 0x40000000u;
         if (tid == 0) hist[a.hist_bins] = 0;
     } else {
         uint32_t *bm_all = smem;
@@ -593,7 +591,6 @@ k_score_dense(ScoreArgs a)
         for (uint32_t i = tid; i < DT_WARPS * DT_WORDS; i += DT_THREADS) bm_all[i] = 0;
     }
     const uint32_t bm_s = (uint32_t)__cvta_generic_to_shared(bm), hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-    const uint32_t dummy_s = (uint32_t)__cvta_generic_to_shared(s_dummy + (ROUTED ? tid : 0));
     const uint32_t dummy_bin = a.hist_bins + 1u + lane;                     // see add_gap_r
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
@@ -678,7 +675,10 @@ k_score_dense(ScoreArgs a)
                         for (int q = 0; q < 8; ++q) {
                             ca[q] = cnt_s | ((v[q] >> 6) & 0x7Cu);         // tile_base is a multiple of 2^13: bits 8..12 = window
                             const bool site = q < 3 ? (q >= qlo && q < qhi) : q < qhi;   // qlo <= 3
-                            old[q] = route_take(site ? ca[q] : dummy_s);
+                            // (measured: sending the other lanes' atomics to per-lane dummy words instead keeps the code
+                            // straight, 16 instructions per tile fewer, but adds a wavefront or two per atomic: same speed)
+                            old[q] = DT_ROW_CAP;
+                            if (site) old[q] = route_take(ca[q]);
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) route_put(old[q], ca[q], v[q]);
@@ -1373,7 +1373,7 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
     // routed: alignment slack + counters and slots + histogram with its overflow bin and 32 dummy words; the histogram of
     // the dense kernel is what fits beside them (sets with a larger gap are flagged for swga_gini_unbounded as always)
     if (routed) {
-        const uint32_t fit = (uint32_t)((227u * 1024u - 6144u - 128u - DT_WARPS * DT_RT_BYTES) / 4u - 33u);   // 39,103
+        const uint32_t fit = (uint32_t)((227u * 1024u - 2048u - 128u - DT_WARPS * DT_RT_BYTES) / 4u - 33u);   // 40,127
         a.hist_bins = std::min(a.hist_bins, fit);
     }
     const size_t smem = routed ? 128ull + (size_t)DT_WARPS * DT_RT_BYTES + 4ull * (a.hist_bins + 33u)
