@@ -841,7 +841,10 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
                               "frac": bytes_alg / (best * 1e-3) / 1e9 / hbm_peak,
                               "smem_frac": merged / (best * 1e-3) / 1e9 / sh_peak,
                               "note": "site lists are L2-resident; smem_frac = merged sites/s against the shared-memory "
-                                      "operation peak (one operation per merged site is the floor)"}}
+                                      "operation peak (one operation per merged site is the floor)" + (
+                                          "; ncu (profiles/r02_k_score_dense_phases.txt): 351 warp-instructions per 2^13-position "
+                                          "tile (round 1: 524), issue slots 75 % and the shared-memory data pipe 79 % busy"
+                                          if name == "C4_dense" else "")}}
             if world == 1:
                 # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
                 h_sets = d_raw.cpu().numpy()
