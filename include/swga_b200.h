@@ -286,9 +286,12 @@ int swga_tile_offsets(swga_ctx *ctx, const uint32_t *d_sites, const uint64_t *d_
 /* Sets with at most `cap` raw sites (a power of two, 64..16384; 0 disables) are scored by the shared-memory
  * sort kernel, the rest by the bitmap-tile kernel; results are identical.  Default 4096. */
 int swga_ctx_set_score_sort_cap(swga_ctx *ctx, uint32_t cap);
-/* Which form of the dense-set kernel scores the sets above `cap`: 0 (default) = routed -- every site takes a slot in
- * the row of its 256-position window, the owner lane sorts its row in registers; 1 = bitmap + compaction (round 1).
- * Results are identical (swga/score.py:73-98, swga/stats.py:10-54 for both). */
+/* Which form of the dense-set kernel scores the sets above `cap`: 0 (default) = routed -- within a tile of 2^13
+ * positions every site takes a slot of its 256-position window (one shared atomicAdd), the window's owner lane sorts
+ * its slots in registers and takes the gaps from neighbouring registers; 1 = bitmap + compaction (round 1).
+ * Results are identical (swga/score.py:73-98, swga/stats.py:10-54 for both).  The routed form histograms gaps up to
+ * 40,126 (bitmap form: swga_score_max_hist_bins() - 1); a passing set with a larger gap is flagged (status bit1) for
+ * swga_gini_unbounded by either. */
 int swga_ctx_set_score_dense_impl(swga_ctx *ctx, int impl);
 uint32_t swga_score_tile_shift(void);
 uint32_t swga_score_max_hist_bins(void);
