@@ -293,6 +293,10 @@ int swga_ctx_set_score_sort_cap(swga_ctx *ctx, uint32_t cap);
  * 40,126 (bitmap form: swga_score_max_hist_bins() - 1); a passing set with a larger gap is flagged (status bit1) for
  * swga_gini_unbounded by either. */
 int swga_ctx_set_score_dense_impl(swga_ctx *ctx, int impl);
+/* Front end of the sparse-set kernel: 0 (default) = routed -- the set's sites are counting-sorted by genome window
+ * (one shared atomicAdd per site, register sorting network per window); genomes above 33.5 Mbp and sets with more
+ * than 16 sites in one window take the merge; 1 = always merge the set's sorted lists (round 1).  Same results. */
+int swga_ctx_set_score_sort_impl(swga_ctx *ctx, int impl);
 uint32_t swga_score_tile_shift(void);
 uint32_t swga_score_max_hist_bins(void);
 int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uint32_t *d_toff, uint32_t n_tiles,

@@ -81,6 +81,7 @@ SIGNATURES = {
     "swga_tile_offsets": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, c_vp, c_vp]),
     "swga_ctx_set_score_sort_cap": (ctypes.c_int, [c_ctx, ctypes.c_uint32]),
     "swga_ctx_set_score_dense_impl": (ctypes.c_int, [c_ctx, ctypes.c_int]),
+    "swga_ctx_set_score_sort_impl": (ctypes.c_int, [c_ctx, ctypes.c_int]),
     "swga_score_tile_shift": (ctypes.c_uint32, []),
     "swga_score_max_hist_bins": (ctypes.c_uint32, []),
     "swga_score_sets": (ctypes.c_int, [c_ctx, c_vp, c_vp, ctypes.c_uint32, ctypes.c_uint32, c_vp, ctypes.c_uint32,

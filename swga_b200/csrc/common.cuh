@@ -58,6 +58,7 @@ struct swga_ctx {
     size_t h_recs_cap = 0;
     DevBuf sort_hist, sort_keys[2], sort_vals[2], score_tmp, bucket_data, bucket_meta;
     uint32_t score_sort_cap = 4096;                    // raw sites per set up to which k_score_sort is used (0 = never)
+    int score_sort_impl = 0;                           // k_score_sort: 0 = routed front end (window counting sort), 1 = always merge the lists
     int score_dense_impl = 0;                          // k_score_dense: 0 = routed (window rows + register sort), 1 = bitmap + compaction
     unsigned long long *part_stats = nullptr;          // inside bucket_meta: exits taken by the last partitioned count
     int stage_timing = 0;                              // record events between the kernels of the partitioned count

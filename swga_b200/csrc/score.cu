@@ -48,6 +48,7 @@ struct ScoreArgs {
     uint32_t *gap_out;
     uint32_t *gap_count;
     uint32_t sort_cap;           // sets with at most this many raw sites are scored by k_score_sort, the rest by k_score
+    uint32_t sort_route;         // k_score_sort: 1 = routed front end (counting sort by window), 0 = always merge the lists
     uint32_t *work;              // [2] dynamic work counters (k_score_sort, k_score)
     const uint32_t *ids;         // set ids this kernel scores (from k_score_classify); NULL = all of 0..S-1
     const uint32_t *n_ids;       // number of entries of ids
@@ -436,8 +437,7 @@ __device__ __forceinline__ void add_gap_r(GapAcc &acc, uint32_t g, uint32_t bin,
 // last site before the window (running maximum over the lanes, `carry` from the tiles before, both as position + 1).
 // FIRST: the tile may hold the first site of the warp's range (carry == 0): that site has no gap and is reported.
 template <int N, int M, bool FIRST>
-__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t lane, uint32_t &carry, uint32_t &first, GapAcc &acc,
-                                           uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
+__device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t lane, uint32_t &carry, uint32_t &first, uint32_t (&g)[M])
 {
     // (last position of my window) + 1, 0 = no site: the largest v + 1 (an empty slot wraps to 0), taken from the UNSORTED
     // values so that the warp scan below does not wait for the sorting network
@@ -468,33 +468,35 @@ __device__ __forceinline__ void owner_gaps(uint32_t (&v)[N], uint32_t lane, uint
             }
         }
     }
+    // g[i] = gap of my i-th site to its predecessor; 0 = no gap here (empty slot, a site two lists share, the first site)
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        // empty slot: into my dummy word; a site two lists share: g = 0 into bin 0 (never read)
         bool site = v[i] != DT_EMPTY;
         if (FIRST && i == 0 && site && pred == 0u) {
             first = v[0] + 1u;
             site = false;
         }
-        const uint32_t g = site ? (i ? v[i] - v[i ? i - 1 : 0] : v[0] + 1u - pred) : 0u;
-        add_gap_r(acc, g, site ? min(g, bins) : dummy_bin, hist_s);
+        g[i] = site ? (i ? v[i] - v[i ? i - 1 : 0] : v[0] + 1u - pred) : 0u;
     }
     carry = max(carry, __shfl_sync(0xffffffffu, run, 31));
 }
 
-// owner_gaps on the first M slots of my window (read and left empty here; `win_s` = address of my slot 0)
+// owner_gaps on the first M slots of my window (read and left empty here; `win_s` = address of my slot 0); every gap goes
+// to the histogram, the slots without one to my dummy word behind it
 template <int M, bool FIRST>
 __device__ __forceinline__ void owner_form(uint32_t win_s, uint32_t lane, uint32_t &carry, uint32_t &first, GapAcc &acc,
                                            uint32_t hist_s, uint32_t bins, uint32_t dummy_bin)
 {
     constexpr int N = M <= 8 ? 8 : 16;
-    uint32_t v[N];
+    uint32_t v[N], g[M];
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = i < M ? lds_u32(win_s + 128u * i) : DT_EMPTY;
 #pragma unroll
     for (int i = 0; i < M; ++i) sts_u32(win_s + 128u * i, DT_EMPTY);
     __syncwarp();
-    owner_gaps<N, M, FIRST>(v, lane, carry, first, acc, hist_s, bins, dummy_bin);
+    owner_gaps<N, M, FIRST>(v, lane, carry, first, g);
+#pragma unroll
+    for (int i = 0; i < M; ++i) add_gap_r(acc, g[i], g[i] ? min(g[i], bins) : dummy_bin, hist_s);
 }
 
 // One tile through the bitmap, every lane walking its own 8 words (any number of sites, with or without a predecessor).
@@ -1102,17 +1104,90 @@ __device__ __forceinline__ T block_reduce_ss(T v, Op op, T ident, T *scratch /* 
     return w;
 }
 
+// ---- routed front end of k_score_sort (round 2) -----------------------------------------------------------------
+// The merge of the set's sorted lists (4 merge-path passes for 9-11 lists) is replaced by the counting sort of the dense
+// kernel, over the WHOLE genome at once: windows of 2^rsh positions (at most RS_W of them; rsh <= 15 so that a position
+// inside its window is a uint16 below 0x8000), every site takes the next slot of its window with one shared atomicAdd,
+// then each warp walks its share of the windows 32 at a time -- lane = window: sort the slots in registers, gaps from
+// neighbouring registers (owner_gaps) -- and appends the gaps to the list the Gini step reads.  A window with more than
+// RS_CAP sites sends the set through the merge (its slots are cleared first); genomes above 2^15 RS_W = 33.5 Mbp too.
+#define RS_W 1024u
+#define RS_CAP 16u
+#define RS_EMPTY16 0xffffu
+#define RS_BYTES (RS_W * 4u + RS_W * RS_CAP * 2u)          // counters + slots (slot-major: slot s of window w at 2 (s RS_W + w))
+
+__device__ __forceinline__ uint32_t lds_s16(uint32_t addr)    // sign-extended: an empty slot reads as DT_EMPTY
+{
+    int32_t v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return (uint32_t)v;
+}
+
+struct SparseAcc {
+    uint32_t cnt, maxgap;
+    unsigned long long sumsq;
+};
+
+// 32 windows (lane = window `w`, slot 0 at win_s) holding at most M sites each: gaps -> acc, and appended to gp
+template <int M, bool FIRST>
+__device__ __forceinline__ void sparse_form(uint32_t win_s, uint32_t wbase, uint32_t lane, uint32_t &carry, uint32_t &first,
+                                            SparseAcc &acc, uint32_t *gp, uint32_t *s_ng)
+{
+    constexpr int N = M <= 8 ? 8 : 16;
+    uint32_t v[N], g[M];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = i < M ? (lds_s16(win_s + 2u * RS_W * i) | wbase) : DT_EMPTY;   // empty | wbase = empty
+#pragma unroll
+    for (int i = 0; i < M; ++i) sts_u16(win_s + 2u * RS_W * i, RS_EMPTY16);
+    owner_gaps<N, M, FIRST>(v, lane, carry, first, g);
+    uint32_t k = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        k += g[i] != 0u;
+        acc.sumsq += (unsigned long long)g[i] * g[i];
+        acc.maxgap = max(acc.maxgap, g[i]);
+    }
+    acc.cnt += k;
+    uint32_t incl = k;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(s_ng, incl);
+    uint32_t idx = __shfl_sync(0xffffffffu, base, 31) + incl - k;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (g[i]) {
+            gp[MS_PHYS(idx)] = g[i];
+            ++idx;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SS_THREADS)
 k_score_sort(ScoreArgs a)
 {
-    extern __shared__ uint32_t smem[];
-    uint32_t *buf = smem;                       // [cap2] positions
-    uint32_t *gaps = smem + MS_PHYS(a.sort_cap + SS_RUN_PAD);  // second buffer; both in the padded layout MS_PHYS
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t bufwords = MS_PHYS(a.sort_cap + SS_RUN_PAD);
+    uint32_t *gaps = smem;                      // second buffer of the merge / the gap list; padded layout MS_PHYS
+    uint32_t *buf = smem + bufwords;            // [cap2] positions; the routed front end's counters and slots lie here too
     __shared__ uint32_t s_src[SC_MAX_LISTS], s_len[SC_MAX_LISTS], s_rb[SC_MAX_LISTS + 1];   // s_rb: run starts, multiples of 16
     __shared__ uint32_t s_nl, s_raw, s_set;
     __shared__ uint32_t r32[SS_WARPS + 1];
     __shared__ unsigned long long r64[SS_WARPS + 1];
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_ng, s_ovf, s_first[SS_WARPS], s_last[SS_WARPS];
+    __shared__ unsigned long long s_H;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    // routed front end: windows of 2^rsh positions, at most RS_W of them
+    uint32_t rsh = DT_SHIFT;
+    while (((a.n_tiles + (1u << (rsh - DT_SHIFT)) - 1u) >> (rsh - DT_SHIFT)) > RS_W) ++rsh;
+    const uint32_t nwin = (a.n_tiles + (1u << (rsh - DT_SHIFT)) - 1u) >> (rsh - DT_SHIFT);
+    const bool can_route = a.sort_route && rsh <= 15u;
+    uint32_t *cnt32 = buf;
+    const uint32_t slots_s = (uint32_t)__cvta_generic_to_shared(buf + RS_W);
+    bool rt_dirty = true;                       // counters / slots need (re-)initialising: the merge and Gini write over them
     for (;;) {
         if (tid == 0) s_set = atomicAdd(a.work, 1u);
         __syncthreads();
@@ -1130,20 +1205,111 @@ k_score_sort(ScoreArgs a)
             }
             s_rb[n] = at;
             s_nl = n; s_raw = raw;
+            s_ng = 0; s_ovf = 0;
+        }
+        if (can_route && rt_dirty) {
+            for (uint32_t i = tid; i < RS_W; i += SS_THREADS) cnt32[i] = 0;
+            for (uint32_t i = tid; i < RS_W * RS_CAP / 2u; i += SS_THREADS) buf[RS_W + i] = 0xffffffffu;
+            rt_dirty = false;
         }
         __syncthreads();
         const uint32_t raw = s_raw, nl = s_nl;
+        uint32_t cnt = 0, maxgap = 0, entries = 0;
+        unsigned long long sumsq = 0, H = 0;
+        uint32_t *pos = buf, *gp = gaps;
+        bool routed = false;
+        if (can_route) {
+            // ---- every site takes a slot of its window ----
+            const uint32_t rmask = (1u << rsh) - 1u;
+            for (uint32_t l = 0; l < nl; ++l) {
+                const uint32_t len = s_len[l];
+                const uint32_t *src = a.sites + s_src[l];
+                for (uint32_t i = tid; i < len; i += SS_THREADS) {
+                    const uint32_t p = __ldg(src + i), w = p >> rsh;
+                    const uint32_t old = atomicAdd(&cnt32[w], 1u);
+                    if (old < RS_CAP) sts_u16(slots_s + 2u * (old * RS_W + w), p & rmask);
+                }
+            }
+            __syncthreads();
+            // ---- each warp its share of the windows, 32 at a time (lane = window) ----
+            const uint32_t NR = (nwin + 31u) / 32u, RPW = (NR + SS_WARPS - 1u) / SS_WARPS;
+            const uint32_t r1 = min(NR, (wq + 1u) * RPW);
+            uint32_t carry = 0, first = 0;                             // (position + 1) of the last / first site of my range
+            SparseAcc acc;
+            acc.cnt = 0; acc.maxgap = 0; acc.sumsq = 0;
+            for (uint32_t r = wq * RPW; r < r1; ++r) {
+                const uint32_t w = r * 32u + lane;
+                uint32_t c = 0;
+                if (w < nwin) {
+                    c = cnt32[w];
+                    cnt32[w] = 0;
+                }
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, c);
+                if (mx == 0u) continue;
+                const uint32_t win_s = slots_s + 2u * w, wbase = w << rsh;
+                if (mx > RS_CAP) {                                     // the set goes through the merge; leave the slots empty
+                    if (c) {
+#pragma unroll
+                        for (uint32_t q = 0; q < RS_CAP; ++q) sts_u16(win_s + 2u * RS_W * q, RS_EMPTY16);
+                    }
+                    if (lane == 0) s_ovf = 1;
+                    continue;
+                }
+#define RS_FORM(M)                                                                              \
+    do {                                                                                        \
+        if (carry == 0u) sparse_form<M, true>(win_s, wbase, lane, carry, first, acc, gaps, &s_ng);   \
+        else sparse_form<M, false>(win_s, wbase, lane, carry, first, acc, gaps, &s_ng);         \
+    } while (0)
+                if (mx <= 4u) {
+                    if (mx <= 2u) RS_FORM(2);
+                    else RS_FORM(4);
+                } else if (mx <= 8u) {
+                    if (mx <= 6u) RS_FORM(6);
+                    else RS_FORM(8);
+                } else if (mx <= 12u) RS_FORM(12);
+                else RS_FORM(16);
+#undef RS_FORM
+            }
+            first = __reduce_max_sync(0xffffffffu, first);             // one lane set it
+            if (lane == 0) { s_first[wq] = first; s_last[wq] = carry; }
+            cnt = acc.cnt; maxgap = acc.maxgap; sumsq = acc.sumsq;
+            __syncthreads();
+            routed = s_ovf == 0u;
+            if (routed) {
+                if (tid == 0) {                                        // gaps between the ranges of consecutive non-empty warps
+                    uint32_t prev = 0, fst = 0, ng = s_ng;
+                    for (uint32_t wv = 0; wv < SS_WARPS; ++wv) {
+                        if (!s_last[wv]) continue;
+                        if (prev) {
+                            const uint32_t d = s_first[wv] - prev;     // both carry the + 1
+                            gaps[MS_PHYS(ng)] = d;
+                            ++ng; ++cnt; maxgap = max(maxgap, d);
+                            sumsq += (unsigned long long)d * d;
+                        } else {
+                            fst = s_first[wv];
+                        }
+                        prev = s_last[wv];
+                    }
+                    s_ng = ng;
+                    s_H = prev ? (unsigned long long)(prev - fst) : 0ull;
+                }
+                __syncthreads();
+                entries = s_ng;
+                H = s_H;
+            }
+        }
+        if (!routed) {
+        rt_dirty = can_route;
         for (uint32_t l = 0; l < nl; ++l) {                                // every list is one sorted run, tail = 0xffffffff
             const uint32_t len = s_len[l], at = s_rb[l], end = s_rb[l + 1];
             const uint32_t *src = a.sites + s_src[l];
             for (uint32_t i = tid; i < end - at; i += SS_THREADS) buf[MS_PHYS(at + i)] = i < len ? src[i] : 0xffffffffu;
         }
         __syncthreads();
-        uint32_t *pos = block_merge_runs(buf, gaps, s_rb, nl);         // sorted positions (duplicates kept)
-        uint32_t *gp = pos == buf ? gaps : buf;
+        pos = block_merge_runs(buf, gaps, s_rb, nl);                   // sorted positions (duplicates kept)
+        gp = pos == buf ? gaps : buf;
         // gaps between distinct neighbours; duplicates become the sentinel, which sorts last
-        uint32_t cnt = 0, maxgap = 0;
-        unsigned long long sumsq = 0;
+        cnt = 0; maxgap = 0; sumsq = 0;
         for (uint32_t i = tid; i < raw; i += SS_THREADS) {
             uint32_t g = 0xffffffffu;
             if (i + 1 < raw) {
@@ -1155,13 +1321,16 @@ k_score_sort(ScoreArgs a)
             }
             gp[MS_PHYS(i)] = g;
         }
+        entries = raw;
+        H = raw ? (unsigned long long)(pos[MS_PHYS(raw - 1)] - pos[0]) : 0ull;
+        }
         const uint32_t n = block_reduce_ss(cnt, OpAddU32(), 0u, r32);
         const uint32_t mx = block_reduce_ss(maxgap, OpMaxU32(), 0u, r32);
         const unsigned long long ssq = block_reduce_ss(sumsq, OpAddU64(), 0ull, r64);
-        const unsigned long long H = raw ? (unsigned long long)(pos[MS_PHYS(raw - 1)] - pos[0]) : 0ull;
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         unsigned long long sum_prefix = 0;
         if (passed && n > 0) {
+            rt_dirty = can_route;                                     // the Gini step works in `pos`
             // Gini's rank-weighted sum  sum_i g_(i) (n - i)  over the ascending gaps.  A counting sort by a coarse key
             // (gap >> shift, SS_BINS bins, in the buffer the positions no longer need) groups the gaps; inside a
             // bin (a handful of gaps) the rank is found by comparing with the bin's other members.  Exact for any
@@ -1176,7 +1345,7 @@ k_score_sort(ScoreArgs a)
                 while ((mx >> shift) >= SS_BINS) ++shift;
                 for (uint32_t i = tid; i < SS_BINS; i += SS_THREADS) cnt[i] = 0;
                 __syncthreads();
-                for (uint32_t i = tid; i < raw; i += SS_THREADS) {
+                for (uint32_t i = tid; i < entries; i += SS_THREADS) {
                     const uint32_t g = gp[MS_PHYS(i)];
                     if (g != 0xffffffffu) atomicAdd(&cnt[g >> shift], 1u);
                 }
@@ -1210,7 +1379,7 @@ k_score_sort(ScoreArgs a)
                     before += mine[q];
                 }
                 __syncthreads();
-                for (uint32_t i = tid; i < raw; i += SS_THREADS) {
+                for (uint32_t i = tid; i < entries; i += SS_THREADS) {
                     const uint32_t g = gp[MS_PHYS(i)];
                     if (g != 0xffffffffu) grouped[atomicAdd(&cnt[g >> shift], 1u)] = g;
                 }
@@ -1228,7 +1397,7 @@ k_score_sort(ScoreArgs a)
                 }
                 sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
             } else {
-                const uint32_t *sg = block_merge_sort(gp, pos, raw);   // ascending gaps
+                const uint32_t *sg = block_merge_sort(gp, pos, entries);   // ascending gaps
                 unsigned long long part = 0;
                 for (uint32_t i = tid; i < n; i += SS_THREADS) part += (unsigned long long)sg[MS_PHYS(i)] * (n - i);
                 sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
@@ -1361,9 +1530,11 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
         SWGA_NOTE_LAUNCH(); k_score_classify<<<grid_for(S, 256), 256, 0, as_stream(stream)>>>(a, ids, n_ids);
         CUDA_TRY(cudaGetLastError());
         a.ids = ids; a.n_ids = n_ids;
-        const size_t smem_s = 8ull * MS_PHYS(a.sort_cap + SS_RUN_PAD);
+        a.sort_route = ctx->score_sort_impl == 0 ? 1u : 0u;
+        const size_t bufb = 4ull * MS_PHYS(a.sort_cap + SS_RUN_PAD);
+        const size_t smem_s = bufb + (a.sort_route ? std::max<size_t>(bufb, RS_BYTES) : bufb);
         CUDA_TRY(cudaFuncSetAttribute(k_score_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem_s + 1024)));
+        const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(16, (226 * 1024) / (smem_s + 1280)));
         const uint32_t grid_s = std::min<uint32_t>(S, (uint32_t)ctx->sm_count * per_sm);
         SWGA_NOTE_LAUNCH(); k_score_sort<<<grid_s, SS_THREADS, smem_s, as_stream(stream)>>>(a);
         CUDA_TRY(cudaGetLastError());
@@ -1393,6 +1564,13 @@ extern "C" int swga_score_sets(swga_ctx *ctx, const uint32_t *d_sites, const uin
     if (routed) k_score_dense<true><<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
     else k_score_dense<false><<<grid, DT_THREADS, smem, as_stream(stream)>>>(a);
     CUDA_TRY(cudaGetLastError());
+    return SWGA_OK;
+}
+
+extern "C" int swga_ctx_set_score_sort_impl(swga_ctx *ctx, int impl)
+{
+    ARG_CHECK(ctx && (impl == 0 || impl == 1));
+    ctx->score_sort_impl = impl;
     return SWGA_OK;
 }
 
