@@ -1193,19 +1193,35 @@ k_score_sort(ScoreArgs a)
         __syncthreads();
         if (s_set >= *a.n_ids) break;
         const uint32_t s = a.ids[s_set];
-        if (tid == 0) {
-            uint32_t n = 0, raw = 0, at = 0;
-            for (uint32_t j = 0; j <= a.max_m && n < SC_MAX_LISTS; ++j) {
-                int32_t id = j < a.max_m ? a.sets[(uint64_t)s * a.max_m + j] : (int32_t)a.bounds_list;
-                if (id < 0) continue;
+        if (wq == 0) {
+            // the set's lists, lane = member (the record bounds last): one round trip for all their extents -- a serial
+            // walk by one thread (two dependent loads per list) held the other warps at the barrier for 16 % of the time
+            int32_t id = -1;
+            if (lane < a.max_m) id = a.sets[(uint64_t)s * a.max_m + lane];
+            else if (lane == a.max_m) id = (int32_t)a.bounds_list;
+            uint32_t lo = 0, len = 0;
+            if (id >= 0) {
                 const uint32_t *row = a.toff + (uint64_t)id * (a.n_tiles + 1);
-                const uint32_t lo = row[0], len = row[a.n_tiles] - lo;
-                s_src[n] = lo; s_len[n] = len; s_rb[n] = at;
-                raw += len; at += (len + MS_E - 1) & ~(MS_E - 1); ++n;
+                lo = row[0];
+                len = row[a.n_tiles] - lo;
             }
-            s_rb[n] = at;
-            s_nl = n; s_raw = raw;
-            s_ng = 0; s_ovf = 0;
+            const uint32_t have = __ballot_sync(0xffffffffu, id >= 0);
+            const uint32_t rank = __popc(have & ((1u << lane) - 1u));
+            const uint32_t padded = id >= 0 ? (len + MS_E - 1) & ~(MS_E - 1) : 0u;
+            uint32_t at = padded, raw = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, at, d);
+                if (lane >= (uint32_t)d) at += o;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, d);
+            if (id >= 0) { s_src[rank] = lo; s_len[rank] = len; s_rb[rank] = at - padded; }
+            if (lane == 31) s_rb[__popc(have)] = at;
+            if (lane == 0) {
+                s_nl = __popc(have); s_raw = raw;
+                s_ng = 0; s_ovf = 0;
+            }
         }
         if (can_route && rt_dirty) {
             for (uint32_t i = tid; i < RS_W; i += SS_THREADS) cnt32[i] = 0;
@@ -1221,14 +1237,31 @@ k_score_sort(ScoreArgs a)
         if (can_route) {
             // ---- every site takes a slot of its window ----
             const uint32_t rmask = (1u << rsh) - 1u;
+            auto route = [&](uint32_t p) {
+                const uint32_t w = p >> rsh;
+                const uint32_t old = atomicAdd(&cnt32[w], 1u);
+                if (old < RS_CAP) sts_u16(slots_s + 2u * (old * RS_W + w), p & rmask);
+            };
+            // the first two sites per thread of list l + 1 are in flight while list l is routed
+            uint32_t v0 = 0, v1 = 0;
+            if (nl) {
+                const uint32_t *src = a.sites + s_src[0];
+                if (tid < s_len[0]) v0 = ld_pinned(src + tid);
+                if (tid + SS_THREADS < s_len[0]) v1 = ld_pinned(src + tid + SS_THREADS);
+            }
             for (uint32_t l = 0; l < nl; ++l) {
                 const uint32_t len = s_len[l];
                 const uint32_t *src = a.sites + s_src[l];
-                for (uint32_t i = tid; i < len; i += SS_THREADS) {
-                    const uint32_t p = __ldg(src + i), w = p >> rsh;
-                    const uint32_t old = atomicAdd(&cnt32[w], 1u);
-                    if (old < RS_CAP) sts_u16(slots_s + 2u * (old * RS_W + w), p & rmask);
+                uint32_t n0 = 0, n1 = 0;
+                if (l + 1 < nl) {
+                    const uint32_t *nsrc = a.sites + s_src[l + 1];
+                    if (tid < s_len[l + 1]) n0 = ld_pinned(nsrc + tid);
+                    if (tid + SS_THREADS < s_len[l + 1]) n1 = ld_pinned(nsrc + tid + SS_THREADS);
                 }
+                if (tid < len) route(v0);
+                if (tid + SS_THREADS < len) route(v1);
+                for (uint32_t i = tid + 2u * SS_THREADS; i < len; i += SS_THREADS) route(__ldg(src + i));
+                v0 = n0; v1 = n1;
             }
             __syncthreads();
             // ---- each warp its share of the windows, 32 at a time (lane = window) ----
