@@ -1174,7 +1174,7 @@ k_score_sort(ScoreArgs a)
     uint32_t *gaps = smem;                      // second buffer of the merge / the gap list; padded layout MS_PHYS
     uint32_t *buf = smem + bufwords;            // [cap2] positions; the routed front end's counters and slots lie here too
     __shared__ uint32_t s_src[SC_MAX_LISTS], s_len[SC_MAX_LISTS], s_rb[SC_MAX_LISTS + 1];   // s_rb: run starts, multiples of 16
-    __shared__ uint32_t s_nl, s_raw, s_set;
+    __shared__ uint32_t s_nl, s_raw, s_set, s_sid;
     __shared__ uint32_t r32[SS_WARPS + 1];
     __shared__ unsigned long long r64[SS_WARPS + 1];
     __shared__ uint32_t s_ng, s_ovf, s_first[SS_WARPS], s_last[SS_WARPS];
@@ -1188,23 +1188,50 @@ k_score_sort(ScoreArgs a)
     uint32_t *cnt32 = buf;
     const uint32_t slots_s = (uint32_t)__cvta_generic_to_shared(buf + RS_W);
     bool rt_dirty = true;                       // counters / slots need (re-)initialising: the merge and Gini write over them
-    for (;;) {
-        if (tid == 0) s_set = atomicAdd(a.work, 1u);
-        __syncthreads();
-        if (s_set >= *a.n_ids) break;
-        const uint32_t s = a.ids[s_set];
+    // Warp 0 carries the NEXT set's descriptor through the current set: the dependent global accesses of its chain (work
+    // counter -> set id -> members -> extents of their lists, ~3 us end to end) are issued one phase of the current set
+    // before their result is needed, instead of in a row at the top of the set with the other warps at the barrier.
+    const uint32_t n_ids = *a.n_ids;
+    uint32_t nx_set = 0xffffffffu, nx_s = 0, nx_lo = 0, nx_len = 0;
+    int32_t nx_id = -1;
+    auto pf_counter = [&]() {                   // lane 0: next work item
+        if (tid == 0) nx_set = atomicAdd(a.work, 1u);
+    };
+    auto pf_setid = [&]() {                     // lane 0: its set id
+        if (tid == 0) nx_s = nx_set < n_ids ? a.ids[nx_set] : 0u;
+    };
+    auto pf_members = [&]() {                   // lane = member (the record bounds last)
         if (wq == 0) {
-            // the set's lists, lane = member (the record bounds last): one round trip for all their extents -- a serial
-            // walk by one thread (two dependent loads per list) held the other warps at the barrier for 16 % of the time
-            int32_t id = -1;
-            if (lane < a.max_m) id = a.sets[(uint64_t)s * a.max_m + lane];
-            else if (lane == a.max_m) id = (int32_t)a.bounds_list;
-            uint32_t lo = 0, len = 0;
-            if (id >= 0) {
-                const uint32_t *row = a.toff + (uint64_t)id * (a.n_tiles + 1);
-                lo = row[0];
-                len = row[a.n_tiles] - lo;
+            nx_set = __shfl_sync(0xffffffffu, nx_set, 0);
+            nx_s = __shfl_sync(0xffffffffu, nx_s, 0);
+            nx_id = -1;
+            if (nx_set < n_ids) {
+                if (lane < a.max_m) nx_id = a.sets[(uint64_t)nx_s * a.max_m + lane];
+                else if (lane == a.max_m) nx_id = (int32_t)a.bounds_list;
             }
+        }
+    };
+    auto pf_extents = [&]() {                   // the extent of every member's list
+        if (wq == 0) {
+            nx_lo = 0; nx_len = 0;
+            if (nx_id >= 0) {
+                const uint32_t *row = a.toff + (uint64_t)nx_id * (a.n_tiles + 1);
+                nx_lo = row[0];
+                nx_len = row[a.n_tiles] - nx_lo;
+            }
+        }
+    };
+    uint32_t pf_done = 0;                       // stages of the next descriptor issued so far (uniform)
+    auto pf_to = [&](uint32_t k) {
+        if (pf_done < 2u && k >= 2u) { pf_setid(); pf_done = 2u; }
+        if (pf_done < 3u && k >= 3u) { pf_members(); pf_done = 3u; }
+        if (pf_done < 4u && k >= 4u) { pf_extents(); pf_done = 4u; }
+    };
+    pf_counter(); pf_setid(); pf_members(); pf_extents();
+    for (;;) {
+        if (wq == 0) {
+            const int32_t id = nx_id;
+            const uint32_t lo = nx_lo, len = nx_len;
             const uint32_t have = __ballot_sync(0xffffffffu, id >= 0);
             const uint32_t rank = __popc(have & ((1u << lane) - 1u));
             const uint32_t padded = id >= 0 ? (len + MS_E - 1) & ~(MS_E - 1) : 0u;
@@ -1219,6 +1246,7 @@ k_score_sort(ScoreArgs a)
             if (id >= 0) { s_src[rank] = lo; s_len[rank] = len; s_rb[rank] = at - padded; }
             if (lane == 31) s_rb[__popc(have)] = at;
             if (lane == 0) {
+                s_set = nx_set; s_sid = nx_s;
                 s_nl = __popc(have); s_raw = raw;
                 s_ng = 0; s_ovf = 0;
             }
@@ -1229,6 +1257,10 @@ k_score_sort(ScoreArgs a)
             rt_dirty = false;
         }
         __syncthreads();
+        if (s_set >= n_ids) break;
+        const uint32_t s = s_sid;
+        pf_counter();
+        pf_done = 1u;
         const uint32_t raw = s_raw, nl = s_nl;
         uint32_t cnt = 0, maxgap = 0, entries = 0;
         unsigned long long sumsq = 0, H = 0;
@@ -1264,6 +1296,7 @@ k_score_sort(ScoreArgs a)
                 v0 = n0; v1 = n1;
             }
             __syncthreads();
+            pf_to(2u);
             // ---- each warp its share of the windows, 32 at a time (lane = window) ----
             const uint32_t NR = (nwin + 31u) / 32u, RPW = (NR + SS_WARPS - 1u) / SS_WARPS;
             const uint32_t r1 = min(NR, (wq + 1u) * RPW);
@@ -1307,6 +1340,7 @@ k_score_sort(ScoreArgs a)
             if (lane == 0) { s_first[wq] = first; s_last[wq] = carry; }
             cnt = acc.cnt; maxgap = acc.maxgap; sumsq = acc.sumsq;
             __syncthreads();
+            pf_to(3u);
             routed = s_ovf == 0u;
             if (routed) {
                 if (tid == 0) {                                        // gaps between the ranges of consecutive non-empty warps
@@ -1333,6 +1367,7 @@ k_score_sort(ScoreArgs a)
         }
         if (!routed) {
         rt_dirty = can_route;
+        pf_to(2u);
         for (uint32_t l = 0; l < nl; ++l) {                                // every list is one sorted run, tail = 0xffffffff
             const uint32_t len = s_len[l], at = s_rb[l], end = s_rb[l + 1];
             const uint32_t *src = a.sites + s_src[l];
@@ -1340,6 +1375,7 @@ k_score_sort(ScoreArgs a)
         }
         __syncthreads();
         pos = block_merge_runs(buf, gaps, s_rb, nl);                   // sorted positions (duplicates kept)
+        pf_to(3u);
         gp = pos == buf ? gaps : buf;
         // gaps between distinct neighbours; duplicates become the sentinel, which sorts last
         cnt = 0; maxgap = 0; sumsq = 0;
@@ -1357,6 +1393,7 @@ k_score_sort(ScoreArgs a)
         entries = raw;
         H = raw ? (unsigned long long)(pos[MS_PHYS(raw - 1)] - pos[0]) : 0ull;
         }
+        pf_to(4u);
         const uint32_t n = block_reduce_ss(cnt, OpAddU32(), 0u, r32);
         const uint32_t mx = block_reduce_ss(maxgap, OpMaxU32(), 0u, r32);
         const unsigned long long ssq = block_reduce_ss(sumsq, OpAddU64(), 0ull, r64);
