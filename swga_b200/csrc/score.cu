@@ -1177,7 +1177,7 @@ k_score_sort(ScoreArgs a)
     __shared__ uint32_t s_nl, s_raw, s_set, s_sid;
     __shared__ uint32_t r32[SS_WARPS + 1];
     __shared__ unsigned long long r64[SS_WARPS + 1];
-    __shared__ uint32_t s_ng, s_ovf, s_first[SS_WARPS], s_last[SS_WARPS];
+    __shared__ uint32_t s_ng, s_ovf, s_first[SS_WARPS], s_last[SS_WARPS], s_rmx[SS_WARPS];
     __shared__ unsigned long long s_H;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     // routed front end: windows of 2^rsh positions, at most RS_W of them
@@ -1394,9 +1394,21 @@ k_score_sort(ScoreArgs a)
         H = raw ? (unsigned long long)(pos[MS_PHYS(raw - 1)] - pos[0]) : 0ull;
         }
         pf_to(4u);
-        const uint32_t n = block_reduce_ss(cnt, OpAddU32(), 0u, r32);
-        const uint32_t mx = block_reduce_ss(maxgap, OpMaxU32(), 0u, r32);
-        const unsigned long long ssq = block_reduce_ss(sumsq, OpAddU64(), 0ull, r64);
+        // the three set-wide statistics in one exchange (two barriers instead of six)
+        uint32_t n = cnt, mx = maxgap;
+        unsigned long long ssq = sumsq;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            n += __shfl_xor_sync(0xffffffffu, n, d);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+        }
+        __syncthreads();
+        if (lane == 0) { r32[wq] = n; s_rmx[wq] = mx; r64[wq] = ssq; }
+        __syncthreads();
+        n = 0; mx = 0; ssq = 0;
+#pragma unroll
+        for (int i = 0; i < SS_WARPS; ++i) { n += r32[i]; mx = max(mx, s_rmx[i]); ssq += r64[i]; }
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         unsigned long long sum_prefix = 0;
         if (passed && n > 0) {
@@ -1473,7 +1485,10 @@ k_score_sort(ScoreArgs a)
                 sum_prefix = block_reduce_ss(part, OpAddU64(), 0ull, r64);
             }
         }
-        if (tid == 0) {
+        // The set's results are in registers of every thread: the last warp's first lane writes them out (double-precision
+        // divisions and a square root) while warp 0 already publishes the next set -- no barrier at the end of a set: every
+        // read of the set's shared-memory state lies before the last barrier above.
+        if (tid == SS_THREADS - 32) {
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             double mean = nan, sd = nan, gini = nan, score = nan;
             if (n > 0) {
@@ -1502,7 +1517,6 @@ k_score_sort(ScoreArgs a)
             a.score[s] = score;
             a.status[s] = (uint8_t)(passed ? 1 : 0);
         }
-        __syncthreads();
     }
 }
 

@@ -163,8 +163,9 @@ def test_batched_scoring_matches_oracle(quirky, oracle):
     from swga_b200 import _lib
     lib, ctx = _lib.load(), _lib.context(0)
     try:
-        for cap in (4096, 0, 256):                                           # sort kernel / bitmap kernel / mixed
+        for cap, sort_impl in ((4096, 0), (4096, 1), (0, 0), (256, 0)):      # sort kernel (routed / merge front end) / dense kernel / mixed
             _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, cap))
+            _lib.check(lib.swga_ctx_set_score_sort_impl(ctx.h, sort_impl))
             for max_fg, interactive in ((36000, False), (3000, False), (0, True)):
                 res = score.score_sets(sl, sets, bgs, max_fg, interactive=interactive)
                 want = _oracle_scores(oracle, locs_of, chr_ends, sets, bgs, max_fg, interactive)
@@ -179,6 +180,7 @@ def test_batched_scoring_matches_oracle(quirky, oracle):
                 assert ((res.status & 2) != 0).any()
     finally:
         _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
+        _lib.check(lib.swga_ctx_set_score_sort_impl(ctx.h, 0))
 
 
 def test_reference_score_kats(oracle):
@@ -271,10 +273,12 @@ def test_scoring_kernels_edge_shapes(oracle):
     bgs = rng.uniform(10, 1e4, len(sets))
     lib, ctx = _lib.load(), _lib.context(0)
     try:
-        # sort cap x dense-kernel form: (0, 1) = every set through the bitmap form of round 1, the rest the routed form
-        for cap, dense_impl in ((4096, 0), (0, 0), (0, 1), (64, 0), (16384, 0)):
+        # sort cap x dense-kernel form x sparse-kernel front end: (0, 1, .) = every set through the bitmap form of round 1,
+        # (., ., 1) = the sparse kernel always merges the lists; otherwise the routed forms (crowded windows fall back)
+        for cap, dense_impl, sort_impl in ((4096, 0, 0), (4096, 0, 1), (0, 0, 0), (0, 1, 0), (64, 0, 0), (16384, 0, 0), (16384, 0, 1)):
             _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, cap))
             _lib.check(lib.swga_ctx_set_score_dense_impl(ctx.h, dense_impl))
+            _lib.check(lib.swga_ctx_set_score_sort_impl(ctx.h, sort_impl))
             for max_fg in (36000, 2 ** 31 - 1):
                 res = score.score_sets(sl, arr, bgs, max_fg)
                 for i, s in enumerate(sets):
@@ -290,6 +294,7 @@ def test_scoring_kernels_edge_shapes(oracle):
     finally:
         _lib.check(lib.swga_ctx_set_score_sort_cap(ctx.h, 4096))
         _lib.check(lib.swga_ctx_set_score_dense_impl(ctx.h, 0))
+        _lib.check(lib.swga_ctx_set_score_sort_impl(ctx.h, 0))
 
 
 def test_config3_config4_full_size(oracle):
