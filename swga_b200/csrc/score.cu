@@ -1321,18 +1321,13 @@ k_score_sort(ScoreArgs a)
                     if (lane == 0) s_ovf = 1;
                     continue;
                 }
-#define RS_FORM(M)                                                                              \
-    do {                                                                                        \
-        if (carry == 0u) sparse_form<M, true>(win_s, wbase, lane, carry, first, acc, gaps, &s_ng);   \
-        else sparse_form<M, false>(win_s, wbase, lane, carry, first, acc, gaps, &s_ng);         \
-    } while (0)
-                if (mx <= 4u) {
-                    if (mx <= 2u) RS_FORM(2);
-                    else RS_FORM(4);
-                } else if (mx <= 8u) {
-                    if (mx <= 6u) RS_FORM(6);
-                    else RS_FORM(8);
-                } else if (mx <= 12u) RS_FORM(12);
+                // one instantiation per form: the "first site of the range" test of owner_gaps is a run-time one here (pred == 0
+                // only while carry == 0); the kernel's code must stay inside the instruction cache (ncu: no_inst 23 % with
+                // twelve instantiations)
+#define RS_FORM(M) sparse_form<M, true>(win_s, wbase, lane, carry, first, acc, gaps, &s_ng)
+                if (mx <= 4u) RS_FORM(4);
+                else if (mx <= 8u) RS_FORM(8);
+                else if (mx <= 12u) RS_FORM(12);
                 else RS_FORM(16);
 #undef RS_FORM
             }
