@@ -864,7 +864,9 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
                                       "operation peak (one operation per merged site is the floor)" + (
                                           "; ncu (profiles/r02_k_score_dense_phases.txt): 351 warp-instructions per 2^13-position "
                                           "tile (round 1: 524), issue slots 75 % and the shared-memory data pipe 79 % busy"
-                                          if name == "C4_dense" else "")}}
+                                          if name == "C4_dense" else
+                                          "; ncu (profiles/r02_k_score_sort_ncu_raw.csv): routed front end 10.5 k warp-instructions "
+                                          "per set (merge of round 1: 16.8 k), issue slots 54 % busy at 25 % occupancy")}}
             if world == 1:
                 # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
                 h_sets = d_raw.cpu().numpy()
