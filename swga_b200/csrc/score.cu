@@ -1178,7 +1178,6 @@ k_score_sort(ScoreArgs a)
     __shared__ uint32_t r32[SS_WARPS + 1];
     __shared__ unsigned long long r64[SS_WARPS + 1];
     __shared__ uint32_t s_ng, s_ovf, s_first[SS_WARPS], s_last[SS_WARPS], s_rmx[SS_WARPS];
-    __shared__ unsigned long long s_H;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     // routed front end: windows of 2^rsh positions, at most RS_W of them
     uint32_t rsh = DT_SHIFT;
@@ -1332,32 +1331,40 @@ k_score_sort(ScoreArgs a)
 #undef RS_FORM
             }
             first = __reduce_max_sync(0xffffffffu, first);             // one lane set it
-            if (lane == 0) { s_first[wq] = first; s_last[wq] = carry; }
-            cnt = acc.cnt; maxgap = acc.maxgap; sumsq = acc.sumsq;
+            // my warp's statistics travel with its first / last site through the barrier that ends the window walk: every
+            // thread then adds up the four warps and the (at most three) gaps between their ranges itself -- no further
+            // exchange for a set that is rejected
+            {
+                uint32_t wn = acc.cnt, wmx = acc.maxgap;
+                unsigned long long wss = acc.sumsq;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    wn += __shfl_xor_sync(0xffffffffu, wn, d);
+                    wmx = max(wmx, __shfl_xor_sync(0xffffffffu, wmx, d));
+                    wss += __shfl_xor_sync(0xffffffffu, wss, d);
+                }
+                if (lane == 0) { s_first[wq] = first; s_last[wq] = carry; r32[wq] = wn; s_rmx[wq] = wmx; r64[wq] = wss; }
+            }
             __syncthreads();
             pf_to(3u);
             routed = s_ovf == 0u;
             if (routed) {
-                if (tid == 0) {                                        // gaps between the ranges of consecutive non-empty warps
-                    uint32_t prev = 0, fst = 0, ng = s_ng;
-                    for (uint32_t wv = 0; wv < SS_WARPS; ++wv) {
-                        if (!s_last[wv]) continue;
-                        if (prev) {
-                            const uint32_t d = s_first[wv] - prev;     // both carry the + 1
-                            gaps[MS_PHYS(ng)] = d;
-                            ++ng; ++cnt; maxgap = max(maxgap, d);
-                            sumsq += (unsigned long long)d * d;
-                        } else {
-                            fst = s_first[wv];
-                        }
-                        prev = s_last[wv];
-                    }
-                    s_ng = ng;
-                    s_H = prev ? (unsigned long long)(prev - fst) : 0ull;
-                }
-                __syncthreads();
+                uint32_t prev = 0, fst = 0;
                 entries = s_ng;
-                H = s_H;
+                for (uint32_t wv = 0; wv < SS_WARPS; ++wv) {
+                    cnt += r32[wv]; maxgap = max(maxgap, s_rmx[wv]); sumsq += r64[wv];
+                    if (!s_last[wv]) continue;
+                    if (prev) {                                        // the gap between the ranges of two warps
+                        const uint32_t d = s_first[wv] - prev;         // both carry the + 1
+                        if (tid == 0) gaps[MS_PHYS(entries)] = d;      // read (Gini) behind a barrier
+                        ++entries; ++cnt; maxgap = max(maxgap, d);
+                        sumsq += (unsigned long long)d * d;
+                    } else {
+                        fst = s_first[wv];
+                    }
+                    prev = s_last[wv];
+                }
+                H = prev ? (unsigned long long)(prev - fst) : 0ull;
             }
         }
         if (!routed) {
@@ -1389,21 +1396,23 @@ k_score_sort(ScoreArgs a)
         H = raw ? (unsigned long long)(pos[MS_PHYS(raw - 1)] - pos[0]) : 0ull;
         }
         pf_to(4u);
-        // the three set-wide statistics in one exchange (two barriers instead of six)
+        // the three set-wide statistics: already totals after the routed front end, else one exchange (two barriers)
         uint32_t n = cnt, mx = maxgap;
         unsigned long long ssq = sumsq;
+        if (!routed) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            n += __shfl_xor_sync(0xffffffffu, n, d);
-            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-            ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+            for (int d = 16; d > 0; d >>= 1) {
+                n += __shfl_xor_sync(0xffffffffu, n, d);
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                ssq += __shfl_xor_sync(0xffffffffu, ssq, d);
+            }
+            __syncthreads();
+            if (lane == 0) { r32[wq] = n; s_rmx[wq] = mx; r64[wq] = ssq; }
+            __syncthreads();
+            n = 0; mx = 0; ssq = 0;
+#pragma unroll
+            for (int i = 0; i < SS_WARPS; ++i) { n += r32[i]; mx = max(mx, s_rmx[i]); ssq += r64[i]; }
         }
-        __syncthreads();
-        if (lane == 0) { r32[wq] = n; s_rmx[wq] = mx; r64[wq] = ssq; }
-        __syncthreads();
-        n = 0; mx = 0; ssq = 0;
-#pragma unroll
-        for (int i = 0; i < SS_WARPS; ++i) { n += r32[i]; mx = max(mx, s_rmx[i]); ssq += r64[i]; }
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         unsigned long long sum_prefix = 0;
         if (passed && n > 0) {
