@@ -1186,7 +1186,10 @@ k_score_sort(ScoreArgs a)
     const bool can_route = a.sort_route && rsh <= 15u;
     uint32_t *cnt32 = buf;
     const uint32_t slots_s = (uint32_t)__cvta_generic_to_shared(buf + RS_W);
-    bool rt_dirty = true;                       // counters / slots need (re-)initialising: the merge and Gini write over them
+    // words of `buf` (counters, then slots) to re-initialise before the next routed set: the merge and the Gini step write
+    // over them (all of them at the start; the grouped Gini step touches its 1,024 bins and n words behind them)
+    constexpr uint32_t RT_WORDS = RS_W + RS_W * RS_CAP / 2u;
+    uint32_t rt_dirty = RT_WORDS;
     // Warp 0 carries the NEXT set's descriptor through the current set: the dependent global accesses of its chain (work
     // counter -> set id -> members -> extents of their lists, ~3 us end to end) are issued one phase of the current set
     // before their result is needed, instead of in a row at the top of the set with the other warps at the barrier.
@@ -1251,9 +1254,11 @@ k_score_sort(ScoreArgs a)
             }
         }
         if (can_route && rt_dirty) {
-            for (uint32_t i = tid; i < RS_W; i += SS_THREADS) cnt32[i] = 0;
-            for (uint32_t i = tid; i < RS_W * RS_CAP / 2u; i += SS_THREADS) buf[RS_W + i] = 0xffffffffu;
-            rt_dirty = false;
+            uint4 *b4 = reinterpret_cast<uint4 *>(buf);               // 16-byte aligned: bufwords is a multiple of 4
+            for (uint32_t i = tid; i < RS_W / 4u; i += SS_THREADS) b4[i] = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = RS_W / 4u + tid; i < (rt_dirty + 3u) / 4u; i += SS_THREADS)
+                b4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            rt_dirty = 0;
         }
         __syncthreads();
         if (s_set >= n_ids) break;
@@ -1368,7 +1373,7 @@ k_score_sort(ScoreArgs a)
             }
         }
         if (!routed) {
-        rt_dirty = can_route;
+        rt_dirty = can_route ? RT_WORDS : 0u;
         pf_to(2u);
         for (uint32_t l = 0; l < nl; ++l) {                                // every list is one sorted run, tail = 0xffffffff
             const uint32_t len = s_len[l], at = s_rb[l], end = s_rb[l + 1];
@@ -1416,7 +1421,7 @@ k_score_sort(ScoreArgs a)
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         unsigned long long sum_prefix = 0;
         if (passed && n > 0) {
-            rt_dirty = can_route;                                     // the Gini step works in `pos`
+            if (can_route) rt_dirty = RT_WORDS;                       // the Gini step works in `pos` (narrowed below)
             // Gini's rank-weighted sum  sum_i g_(i) (n - i)  over the ascending gaps.  A counting sort by a coarse key
             // (gap >> shift, SS_BINS bins, in the buffer the positions no longer need) groups the gaps; inside a
             // bin (a handful of gaps) the rank is found by comparing with the bin's other members.  Exact for any
@@ -1459,6 +1464,7 @@ k_score_sort(ScoreArgs a)
                 fullest = block_reduce_ss(fullest, OpMaxU32(), 0u, r32);
             }
             if (fits && fullest <= SS_BIN_CROWD) {
+                if (can_route && routed) rt_dirty = min(RT_WORDS, SS_BINS + n + 8u);   // bins + grouped gaps only
 #pragma unroll
                 for (int q = 0; q < (int)(SS_BINS / SS_THREADS); ++q) {
                     cnt[tid * (SS_BINS / SS_THREADS) + q] = before;      // start of the bin; the scatter turns it into its end
