@@ -563,7 +563,7 @@ k_score_dense(ScoreArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_list[SC_MAX_LISTS];
-    __shared__ uint32_t s_nlists, s_set;
+    __shared__ uint32_t s_nlists, s_set, s_rawsites;
     __shared__ uint32_t s_first[DT_WARPS], s_last[DT_WARPS];              // (position + 1) of the first / last site of a warp's range
     __shared__ uint32_t s_red32[DT_WARPS + 1], s_scan[DT_WARPS + 1];
     __shared__ unsigned long long s_red64[DT_WARPS + 1];
@@ -597,7 +597,6 @@ k_score_dense(ScoreArgs a)
     for (uint32_t i = tid; i < a.hist_bins; i += DT_THREADS) hist[i] = 0;
     __syncthreads();
 
-    const uint32_t tpw = (a.n_tiles + DT_WARPS - 1) / DT_WARPS;            // tiles per warp
     for (;;) {
         if (tid == 0) s_set = atomicAdd(a.work + 1, 1u);
         __syncthreads();
@@ -611,14 +610,33 @@ k_score_dense(ScoreArgs a)
             }
             s_list[n++] = a.bounds_list;
             s_nlists = n;
+            if constexpr (ROUTED) {
+                uint32_t raw = 0;
+                for (uint32_t l = 0; l < n; ++l) {
+                    const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1);
+                    raw += r[a.n_tiles] - r[0];
+                }
+                s_rawsites = raw;
+            }
         }
         __syncthreads();
         const uint32_t nl = s_nlists;
+        // Routed variant: a thin set is walked in COARSE tiles of 8 or 64 fine ones (windows of 2^11 / 2^14 positions) so that a
+        // tile still holds some 64+ sites -- per-tile costs are fixed, and a 7,000-site set spent them on 2,808 tiles of 2.5
+        // sites (1.2 M sets/s; 50 times the time per site of a 2,000-site set in k_score_sort).
+        uint32_t csh = 0;
+        if constexpr (ROUTED) {
+            const uint32_t per_tile = s_rawsites / a.n_tiles;
+            csh = per_tile >= 32u ? 0u : (per_tile >= 4u ? 3u : 6u);
+        }
+        const uint32_t n_ct = (a.n_tiles + (1u << csh) - 1u) >> csh;          // (coarse) tiles of the set
+        const uint32_t tpw = (n_ct + DT_WARPS - 1) / DT_WARPS;                // tiles per warp
+        auto fine = [&](uint32_t t) { return min(a.n_tiles, t << csh); };      // first fine tile of (coarse) tile t
 
         GapAcc acc;
         acc.cnt = 0; acc.maxgap = 0; acc.sumsq = 0;
         uint32_t carry = 0, first = 0;                                     // (position + 1); 0 = none yet
-        const uint32_t t0 = min(a.n_tiles, warp * tpw), t1 = min(a.n_tiles, t0 + tpw);
+        const uint32_t t0 = min(n_ct, warp * tpw), t1 = min(n_ct, t0 + tpw);
         // Software pipeline over the warp's tiles.  Lane = (list lane / L, part lane % L), L = 4, 3 or 2 lanes per list for up
         // to 8, 10 or 16 lists: it reads two aligned 16-byte chunks of its list's segment of a tile (part p: the chunks at
         // aligned element offsets 8 p and 8 p + 4), i.e. the first 8 L - 3 .. 8 L sites of every list in ONE load
@@ -631,9 +649,9 @@ k_score_dense(ScoreArgs a)
         const uint32_t *row = a.toff + (uint64_t)s_list[mylist < nl ? mylist : 0] * (a.n_tiles + 1);
         uint32_t b0 = 0, b1 = 0, b2 = 0;                                   // row[t], row[t + 1], row[t + 2] of my list
         if (mylist < nl && t0 < t1) {
-            b0 = row[t0];
-            b1 = row[min(a.n_tiles, t0 + 1)];
-            b2 = row[min(a.n_tiles, t0 + 2)];
+            b0 = row[fine(t0)];
+            b1 = row[fine(t0 + 1)];
+            b2 = row[fine(t0 + 2)];
         }
         uint4 pa = make_uint4(0, 0, 0, 0), pb = pa;                        // chunks of the current tile
         if (b1 > b0) {
@@ -650,15 +668,15 @@ k_score_dense(ScoreArgs a)
                 na = ld_pinned4(c);
                 nb4 = ld_pinned4(c + 1);
             }
-            const uint32_t b3 = (mylist < nl && t + 1 < t1) ? ld_pinned(row + min(a.n_tiles, t + 3)) : b2;
+            const uint32_t b3 = (mylist < nl && t + 1 < t1) ? ld_pinned(row + fine(t + 3)) : b2;
             const uint32_t tile_base = t << DT_SHIFT;
             const uint32_t covered = cov8 - (lo & 3u);                   // sites of my list the chunks hold
             bool any = __any_sync(0xffffffffu, len != 0);
             uint32_t need = __ballot_sync(0xffffffffu, len > covered && half == 0u);   // lists (their first lane) with sites beyond the chunks
             if (nl > 16) {                                                 // lists no lane owns
                 for (uint32_t l = 16; l < nl && !any; ++l) {
-                    const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
-                    any = r[1] > r[0];
+                    const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1);
+                    any = r[fine(t + 1)] > r[fine(t)];
                 }
             }
             if constexpr (ROUTED) {
@@ -675,7 +693,7 @@ k_score_dense(ScoreArgs a)
                         uint32_t ca[8], old[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            ca[q] = cnt_s | ((v[q] >> 6) & 0x7Cu);         // tile_base is a multiple of 2^13: bits 8..12 = window
+                            ca[q] = cnt_s | ((v[q] >> (6u + csh)) & 0x7Cu);   // the tile starts at a multiple of its size: 5 bits = window
                             const bool site = q < 3 ? (q >= qlo && q < qhi) : q < qhi;   // qlo <= 3
                             // (measured: sending the other lanes' atomics to per-lane dummy words instead keeps the code
                             // straight, 16 instructions per tile fewer, but adds a wavefront or two per atomic: same speed)
@@ -690,15 +708,15 @@ k_score_dense(ScoreArgs a)
                         need &= need - 1;
                         const uint32_t lo_l = __shfl_sync(0xffffffffu, lo, l), len_l = __shfl_sync(0xffffffffu, len, l);
                         for (uint32_t i = cov8 - (lo_l & 3u) + lane; i < len_l; i += 32) {
-                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
+                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> (6u + csh)) & 0x7Cu);
                             route_put(route_take(ca), ca, v);
                         }
                     }
                     for (uint32_t l = 16; l < nl; ++l) {                   // lists no lane owns
-                        const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1) + t;
-                        const uint32_t lo_l = r[0], len_l = r[1] - lo_l;
+                        const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1);
+                        const uint32_t lo_l = r[fine(t)], len_l = r[fine(t + 1)] - lo_l;
                         for (uint32_t i = lane; i < len_l; i += 32) {
-                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> 6) & 0x7Cu);
+                            const uint32_t v = __ldg(a.sites + lo_l + i), ca = cnt_s | ((v >> (6u + csh)) & 0x7Cu);
                             route_put(route_take(ca), ca, v);
                         }
                     }
@@ -719,7 +737,8 @@ k_score_dense(ScoreArgs a)
                     __syncwarp();
                     TileState st;
                     st.carry = carry; st.first = first; st.cnt = 0; st.maxgap = acc.maxgap; st.sumsq = acc.sumsq;
-                    st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, t, bm, hist_s, st);
+                    for (uint32_t f = fine(t); f < fine(t + 1); ++f)       // the bitmap holds one fine tile
+                        st = dense_tile_slow(a.sites, a.toff, a.n_tiles, a.hist_bins, s_list, nl, f, bm, hist_s, st);
                     carry = st.carry; first = st.first; acc.maxgap = st.maxgap; acc.sumsq = st.sumsq;
                     uint4 *all = reinterpret_cast<uint4 *>(bm) + 4 * lane;
 #pragma unroll
