@@ -568,6 +568,7 @@ k_score_dense(ScoreArgs a)
     __shared__ uint32_t s_red32[DT_WARPS + 1], s_scan[DT_WARPS + 1];
     __shared__ unsigned long long s_red64[DT_WARPS + 1];
     __shared__ GapAcc s_cross;
+    __shared__ uint32_t s_tot_first, s_tot_last;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // bitmap variant: [DT_WARPS][DT_WORDS] bitmaps, [DT_WARPS][DT_LIST_CAP] compact lists (uint16), histogram.
@@ -602,22 +603,22 @@ k_score_dense(ScoreArgs a)
         __syncthreads();
         if (s_set >= *a.n_ids) break;
         const uint32_t s = a.ids[s_set];
-        if (tid == 0) {
-            uint32_t n = 0;
-            for (uint32_t j = 0; j < a.max_m && n < SC_MAX_LISTS - 1; ++j) {
-                const int32_t id = a.sets[(uint64_t)s * a.max_m + j];
-                if (id >= 0) s_list[n++] = (uint32_t)id;
+        if (warp == 0) {
+            // the set's lists, lane = member (the record bounds last), and -- routed variant -- their total length: one round
+            // trip for the whole warp instead of a serial walk by one thread
+            int32_t id = -1;
+            if (lane < a.max_m) id = a.sets[(uint64_t)s * a.max_m + lane];
+            else if (lane == a.max_m) id = (int32_t)a.bounds_list;
+            uint32_t raw = 0;
+            if (ROUTED && id >= 0) {
+                const uint32_t *r = a.toff + (uint64_t)id * (a.n_tiles + 1);
+                raw = r[a.n_tiles] - r[0];
             }
-            s_list[n++] = a.bounds_list;
-            s_nlists = n;
-            if constexpr (ROUTED) {
-                uint32_t raw = 0;
-                for (uint32_t l = 0; l < n; ++l) {
-                    const uint32_t *r = a.toff + (uint64_t)s_list[l] * (a.n_tiles + 1);
-                    raw += r[a.n_tiles] - r[0];
-                }
-                s_rawsites = raw;
-            }
+            const uint32_t have = __ballot_sync(0xffffffffu, id >= 0);
+            if (id >= 0) s_list[__popc(have & ((1u << lane) - 1u))] = (uint32_t)id;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) raw += __shfl_xor_sync(0xffffffffu, raw, d);
+            if (lane == 0) { s_nlists = __popc(have); s_rawsites = raw; }
         }
         __syncthreads();
         const uint32_t nl = s_nlists;
@@ -871,34 +872,61 @@ k_score_dense(ScoreArgs a)
             b0 = b1; b1 = b2; b2 = b3;
             pa = na; pb = nb4;
         }
-        // ---- the set: gaps between the ranges of consecutive non-empty warps, then block reductions ----
+        // ---- the set: every warp's partial statistics and first / last site meet in warp 0 (lane = warp): the gaps between
+        // the ranges of consecutive non-empty warps, the totals -- two barriers for all of it ----
         first = __reduce_max_sync(0xffffffffu, first);                    // one lane set it
-        if (lane == 0) { s_first[warp] = first; s_last[warp] = carry; }
-        __syncthreads();
-        if (tid == 0) {
-            GapAcc x;
-            x.cnt = 0; x.maxgap = 0; x.sumsq = 0;
-            uint32_t prev = 0;
-            for (uint32_t wv = 0; wv < DT_WARPS; ++wv) {
-                if (!s_last[wv]) continue;
-                if (prev) {
-                    const uint32_t gap = s_first[wv] - prev;              // both carry the + 1
-                    if constexpr (ROUTED) add_gap_r(x, gap, min(gap, a.hist_bins), hist_s);
-                    else add_gap(x, gap, hist_s, a.hist_bins);
-                }
-                prev = s_last[wv];
+        {
+            uint32_t wn = acc.cnt, wmx = acc.maxgap;
+            unsigned long long wss = acc.sumsq;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                wn += __shfl_xor_sync(0xffffffffu, wn, d);
+                wmx = max(wmx, __shfl_xor_sync(0xffffffffu, wmx, d));
+                wss += __shfl_xor_sync(0xffffffffu, wss, d);
             }
-            s_cross = x;
-            if constexpr (ROUTED) hist[0] = 0;                            // took the sites two lists share (add_gap_r)
+            if (lane == 0) { s_first[warp] = first; s_last[warp] = carry; s_red32[warp] = wn; s_scan[warp] = wmx; s_red64[warp] = wss; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            static_assert(DT_WARPS == 32, "lane = warp below");
+            const uint32_t f = s_first[lane], l = s_last[lane];
+            uint32_t tn = s_red32[lane], tmx = s_scan[lane];
+            unsigned long long tss = s_red64[lane];
+            uint32_t pl = l;                                               // last site of the ranges up to mine (position + 1)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) pl = max(pl, __shfl_up_sync(0xffffffffu, pl, d));
+            pl = __shfl_up_sync(0xffffffffu, pl, 1);
+            if (lane == 0) pl = 0;
+            if (l && pl) {                                                 // the gap between my range and the one before it
+                const uint32_t gap = f - pl;                               // both carry the + 1
+                GapAcc x;
+                x.cnt = 0; x.maxgap = 0; x.sumsq = 0;
+                if constexpr (ROUTED) add_gap_r(x, gap, min(gap, a.hist_bins), hist_s);
+                else add_gap(x, gap, hist_s, a.hist_bins);
+                tn += 1u; tmx = max(tmx, gap); tss += x.sumsq;
+            }
+            uint32_t fmin = l ? f : 0xffffffffu, lmax = l;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                tn += __shfl_xor_sync(0xffffffffu, tn, d);
+                tmx = max(tmx, __shfl_xor_sync(0xffffffffu, tmx, d));
+                tss += __shfl_xor_sync(0xffffffffu, tss, d);
+                fmin = min(fmin, __shfl_xor_sync(0xffffffffu, fmin, d));
+                lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+            }
+            if (lane == 0) {
+                s_cross.cnt = tn; s_cross.maxgap = tmx; s_cross.sumsq = tss;
+                s_tot_first = fmin; s_tot_last = lmax;
+                if constexpr (ROUTED) hist[0] = 0;                        // (dummy-free: never written; kept for safety)
+            }
         }
         __syncthreads();
         // number of gaps: counted per gap (bitmap variant) or the sum of the histogram incl. its overflow bin (routed)
         uint32_t n = 0;
-        if constexpr (!ROUTED) n = block_reduce_dt(acc.cnt, OpAddU32(), 0u, s_red32) + s_cross.cnt;
-        const uint32_t mx = max(block_reduce_dt(acc.maxgap, OpMaxU32(), 0u, s_red32), s_cross.maxgap);
-        const unsigned long long ssq = block_reduce_dt(acc.sumsq, OpAddU64(), 0ull, s_red64) + s_cross.sumsq;
-        const uint32_t fst1 = block_reduce_dt(first ? first : 0xffffffffu, OpMinU32(), 0xffffffffu, s_red32);
-        const uint32_t lst1 = block_reduce_dt(carry, OpMaxU32(), 0u, s_red32);
+        if constexpr (!ROUTED) n = s_cross.cnt;
+        const uint32_t mx = s_cross.maxgap;
+        const unsigned long long ssq = s_cross.sumsq;
+        const uint32_t fst1 = s_tot_first, lst1 = s_tot_last;
         const unsigned long long H = lst1 ? (unsigned long long)(lst1 - fst1) : 0ull;
         const bool passed = a.interactive || mx <= a.max_fg_bind_dist;
         const bool hist_ok = mx < a.hist_bins;
