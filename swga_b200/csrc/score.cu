@@ -622,13 +622,15 @@ k_score_dense(ScoreArgs a)
         }
         __syncthreads();
         const uint32_t nl = s_nlists;
-        // Routed variant: a thin set is walked in COARSE tiles of 8 or 64 fine ones (windows of 2^11 / 2^14 positions) so that a
-        // tile still holds some 64+ sites -- per-tile costs are fixed, and a 7,000-site set spent them on 2,808 tiles of 2.5
-        // sites (1.2 M sets/s; 50 times the time per site of a 2,000-site set in k_score_sort).
+        // Routed variant: a thin set is walked in COARSE tiles of 8 or 64 fine ones (windows of 2^11 / 2^14 positions): per-tile
+        // costs are fixed (~350 instructions), and a 7,000-site set spent them on 2,808 tiles of 2.5 sites (1.2 M sets/s; 50
+        // times the time per site of a 2,000-site set in k_score_sort; 4.7 M sets/s with 351 tiles of 20).  The thresholds keep
+        // a window below ~1 site on average: a window that overflows sends ALL fine tiles of its coarse tile through the
+        // bitmap (measured with tiles of 160 sites: 2 % of the sets met one, and lost more than the coarser walk gained).
         uint32_t csh = 0;
         if constexpr (ROUTED) {
             const uint32_t per_tile = s_rawsites / a.n_tiles;
-            csh = per_tile >= 32u ? 0u : (per_tile >= 4u ? 3u : 6u);
+            csh = per_tile >= 8u ? 0u : (per_tile >= 1u ? 3u : 6u);
         }
         const uint32_t n_ct = (a.n_tiles + (1u << csh) - 1u) >> csh;          // (coarse) tiles of the set
         const uint32_t tpw = (n_ct + DT_WARPS - 1) / DT_WARPS;                // tiles per warp
