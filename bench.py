@@ -52,6 +52,7 @@ def parse_args():
                     help="reference arm: shrink the sample so that all timed steps fit this many seconds")
     ap.add_argument("--score-sets", type=float, default=1e7, help="candidate sets of the 'typical' scoring workload")
     ap.add_argument("--score-sets-dense", type=float, default=1e6, help="candidate sets of the C4-dense scoring workload")
+    ap.add_argument("--score-sets-thin", type=float, default=1e6, help="candidate sets of the thin-set scoring workload (~7,200 sites per set)")
     ap.add_argument("--merge", default="peer", choices=["peer", "multicast", "nccl"],
                     help="cross-GPU merge: the fused kernel over peer pointers (default; measured fastest), the same kernel with "
                          "the reduction inside the NVSwitch (multimem.ld_reduce / multimem.st), or NCCL all_reduce + finalize "
@@ -770,6 +771,7 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
     collective.  Workloads on the 23 Mbp AT-rich foreground (configs[3]):
       C4_dense  SURVEY 8(d)'s C4 primers: the 200 most frequent 8..12-mers (~2 x 10^5 unique sites per set)
       typical   200 12-mers of ~400 sites each (the scale of swga's default min_fg_bind = 1e-5 * fg_length)
+      thin      200 12-mers of ~1,000 sites each (~7,200 sites per set: the dense kernel's coarse tiles)
     each with the default max_fg_bind_dist = 36000 and with no early reject (every set needs Gini)."""
     import numpy as np
     import torch
@@ -786,6 +788,7 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
     t12 = tabs.table(12)
     order = np.argsort(-t12.astype(np.int64), kind="stable")
     lo = int(np.searchsorted(-t12[order].astype(np.int64), -400))
+    lo_thin = int(np.searchsorted(-t12[order].astype(np.int64), -1000))
     c4 = workloads.top_primers(tabs, 5, 12, 200)
     c4_seqs = [kmers.codes_to_kmers([c], k)[0] for k, c, _ in c4]
 
@@ -803,6 +806,8 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
     variants = {
         "C4_dense": (c4_seqs, int(args.score_sets_dense), sl_dense),
         "typical_400_sites": (kmers.codes_to_kmers(order[lo:lo + 200], 12), int(args.score_sets), None),
+        # between the two: ~7,200 sites per set, above the sparse kernel's 4,096 (thin sets in the dense kernel: coarse tiles)
+        "thin_1000_sites": (kmers.codes_to_kmers(order[lo_thin:lo_thin + 200], 12), int(args.score_sets_thin), None),
     }
     recs = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -855,7 +860,7 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
                  "mean_unique_sites_per_set": float(L.to(torch.float64).mean()) if S_r else 0.0,
                  "passed_frac": float((st & 1).to(torch.float64).mean()) if S_r else 0.0,
                  "merged_sites_per_s": merged / best * 1e3,
-                 "roofline": {"kernel": "k_score_dense" if name == "C4_dense" else "k_score_sort", "bound": "smem",
+                 "roofline": {"kernel": "k_score_sort" if name == "typical_400_sites" else "k_score_dense", "bound": "smem",
                               "bytes_alg_per_set": bytes_alg / max(S_r, 1),
                               "achieved": bytes_alg / (best * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": bytes_alg / (best * 1e-3) / 1e9 / hbm_peak,
@@ -866,7 +871,10 @@ def scoring_extra(args, dev, rank, world, rank_max, barrier, sh_peak, hbm_peak):
                                           "tile (round 1: 524), issue slots 75 % and the shared-memory data pipe 79 % busy"
                                           if name == "C4_dense" else
                                           "; ncu (profiles/r02_k_score_sort_ncu_raw.csv): routed front end 10.5 k warp-instructions "
-                                          "per set (merge of round 1: 16.8 k), issue slots 54 % busy at 25 % occupancy")}}
+                                          "per set (merge of round 1: 16.8 k), issue slots 54 % busy at 25 % occupancy"
+                                          if name == "typical_400_sites" else
+                                          "; thin sets: coarse tiles of 8 fine ones, 142 k warp-instructions per set (per-tile cost "
+                                          "is fixed; round 1 walked 2,808 fine tiles: 1.2 M sets/s)")}}
             if world == 1:
                 # end to end through the host API: set array and bg_dist_mean from host memory, results back to numpy
                 h_sets = d_raw.cpu().numpy()
