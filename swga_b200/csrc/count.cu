@@ -130,11 +130,10 @@ __device__ __forceinline__ uint32_t rc_code(uint32_t x, int k)
     return r ^ (0xAAAAAAAAu >> (32 - 2 * k));
 }
 
-__global__ void __launch_bounds__(256)
-k_fold(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int kmin, int kmax, TableOffs offs,
-       uint64_t total)
+__device__ __forceinline__ void fold_small(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int kmin, int kmax,
+                                           const TableOffs &offs, uint64_t total, uint32_t block)
 {
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t i = block * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
     int k = kmin;
     while (k < kmax && i >= offs.off[k + 1]) ++k;
@@ -150,13 +149,12 @@ k_fold(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int kmin,
 // and its reverse complement [rc(B)][rc(M)][rc(A)], so the block of middle value M (M <= rc(M)) loads the two
 // 64 x 64 tiles (.., M, ..) and (.., rc(M), ..) with coalesced 256-byte rows and finds every partner in shared
 // memory.  k_fold reads the partner of every code with a stride of 4^(k-1) words: one sector per lane.
-__global__ void __launch_bounds__(256)
-k_fold_tiled(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int k)
+__device__ __forceinline__ void fold_tile(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int k, uint32_t M)
 {
     __shared__ uint32_t t1[64][65], t2[64][65];
     __shared__ uint8_t rc3[64];                                // reverse complement of a 3-digit code
     const int md = k - 6, sh = 2 * (k - 3);
-    const uint32_t M = blockIdx.x, rM = md ? rc_code(M, md) : 0u;
+    const uint32_t rM = md ? rc_code(M, md) : 0u;
     if (M > rM) return;                                        // handled by the block of rc(M)
     const bool self = M == rM;
     if (threadIdx.x < 64) rc3[threadIdx.x] = (uint8_t)rc_code(threadIdx.x, 3);
@@ -185,6 +183,25 @@ k_fold_tiled(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int
             canon[x] = x < r ? v + pv : (x == r ? v : 0u);
         }
     }
+}
+
+// The whole fold in ONE launch (four before: k_fold + one k_fold_tiled per large table, ~50 us per genome of which the
+// three small launches were mostly ramp and tail): the blocks of the largest table come first, then the tables below it
+// down to k_split, then the one-thread-per-code blocks of the tables below k_split.
+__global__ void __launch_bounds__(256)
+k_fold_all(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int kmin, int kmax, int k_split, TableOffs offs,
+           uint64_t total_small)
+{
+    uint32_t b = blockIdx.x;
+    for (int k = kmax; k >= k_split; --k) {
+        const uint32_t nb = 1u << (2 * (k - 6));
+        if (b < nb) {
+            fold_tile(fwd + offs.off[k], canon + offs.off[k], k, b);
+            return;
+        }
+        b -= nb;
+    }
+    fold_small(fwd, canon, kmin, min(kmax, k_split - 1), offs, total_small, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,16 +482,15 @@ extern "C" int swga_fold_canonical(swga_ctx *ctx, int kmin, int kmax, const uint
     ARG_CHECK(ctx && d_fwd && d_canon && d_fwd != d_canon);
     TRY(check_k(kmin, kmax));
     const TableOffs offs = swga_make_offs(kmin, kmax);
-    // small tables: one thread per code; tables of k >= 10 (94 % of the codes for 5..12): tiled transpose
+    // small tables: one thread per code; tables of k >= 10 (94 % of the codes for 5..12): tiled transpose; one launch
     const int k_split = std::max(kmin, 10);
+    uint64_t total_small = 0, blocks = 0;
     if (kmin < k_split) {
-        const int k_hi = std::min(kmax, k_split - 1);
-        const uint64_t total = swga_tables_words(kmin, k_hi);
-        SWGA_NOTE_LAUNCH(); k_fold<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, k_hi, offs, total);
+        total_small = swga_tables_words(kmin, std::min(kmax, k_split - 1));
+        blocks += (total_small + 255) / 256;
     }
-    for (int k = k_split; k <= kmax; ++k) {
-        SWGA_NOTE_LAUNCH(); k_fold_tiled<<<1u << (2 * (k - 6)), 256, 0, as_stream(stream)>>>(d_fwd + offs.off[k], d_canon + offs.off[k], k);
-    }
+    for (int k = k_split; k <= kmax; ++k) blocks += 1ull << (2 * (k - 6));
+    SWGA_NOTE_LAUNCH(); k_fold_all<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d_fwd, d_canon, kmin, kmax, k_split, offs, total_small);
     CUDA_TRY(cudaGetLastError());
     return SWGA_OK;
 }

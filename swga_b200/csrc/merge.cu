@@ -69,8 +69,10 @@ k_merge_finalize(PeerBlocks blocks, TableOffs offs, int kmax, int depth, uint64_
                     const uint4 m = reinterpret_cast<const uint4 *>(marg)[i];
                     s.x += m.x; s.y += m.y; s.z += m.z; s.w += m.w;
                 }
+                if (WORLD > 1 || lv > 0) {                     // one rank, top level: the word already holds its value
 #pragma unroll
-                for (int p = 0; p < WORLD; ++p) st_peer(blocks.p[p] + off + 4ull * i, s);
+                    for (int p = 0; p < WORLD; ++p) st_peer(blocks.p[p] + off + 4ull * i, s);
+                }
                 out[i] = s.x + s.y + s.z + s.w;
             }
         } else if (threadIdx.x == 0) {                         // n == 1: the last level of the span
