@@ -181,8 +181,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
-
-    def run(self):
+        self.nv = self.h = self.mx = None
+        # NVML is opened HERE, before the timed region: at N = 8 ten steps last 11 ms, and a sampler that first had to
+        # initialise the library and look its device up came back with no sample at all
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -202,7 +203,16 @@ class ClockSampler(threading.Thread):
                         h = None
             if h is None:
                 h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nv, self.h = nv, h
+        except Exception as e:
+            self.error = repr(e)
+
+    def run(self):
+        try:
+            nv, h, mx = self.nv, self.h, self.mx
+            if nv is None:
+                raise RuntimeError(getattr(self, "error", "NVML unavailable"))
             while not self.stop_flag:
                 clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 try:
@@ -210,7 +220,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append((clk, mx, int(r)))
-                time.sleep(0.002)
+                time.sleep(0.001)
         except Exception as e:                      # NVML missing: fall back to nvidia-smi (slow, few samples)
             self.error = repr(e)
             q = "clocks.sm,clocks.max.sm"
