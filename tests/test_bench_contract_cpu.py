@@ -33,3 +33,20 @@ def test_other_ranks_of_the_reference_arm_do_nothing():
                           "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120,
                          env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert out.returncode == 0 and out.stdout.decode().strip() == ""
+
+
+def test_clock_sampler_without_a_gpu_reports_no_samples():
+    """The sampler opens NVML in its constructor (before the timed region); on a box without a GPU it must neither
+    raise nor hang, and its summary keeps the keys of the bench line's `clocks` object."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    s.stop_flag = True
+    s.join(timeout=10)
+    assert not s.is_alive()
+    c = s.summary()
+    assert set(c) == {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    assert c["samples"] == len(s.samples) and (c["samples"] > 0 or c["sm_mhz"] is None)
