@@ -148,7 +148,7 @@ __device__ __forceinline__ void fold_small(const uint32_t *__restrict__ fwd, uin
 // The same for ONE large table (k >= 7), as a tiled transpose: a code is [A: 3 digits][M: k-6 digits][B: 3 digits]
 // and its reverse complement [rc(B)][rc(M)][rc(A)], so the block of middle value M (M <= rc(M)) loads the two
 // 64 x 64 tiles (.., M, ..) and (.., rc(M), ..) with coalesced 256-byte rows and finds every partner in shared
-// memory.  k_fold reads the partner of every code with a stride of 4^(k-1) words: one sector per lane.
+// memory.  (fold_small reads the partner of every code with a stride of 4^(k-1) words: one sector per lane.)
 __device__ __forceinline__ void fold_tile(const uint32_t *__restrict__ fwd, uint32_t *__restrict__ canon, int k, uint32_t M)
 {
     __shared__ uint32_t t1[64][65], t2[64][65];
